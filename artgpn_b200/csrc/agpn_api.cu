@@ -1,0 +1,640 @@
+// C ABI of libartgpn_b200.so (see include/artgpn_b200.h for the contract and the reference
+// code each entry point replaces).  Host-side orchestration only: context, workspace, kernel
+// launches.  No torch types; streams arrive as void*.
+#include "../../include/artgpn_b200.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "agpn_assemble.cuh"
+#include "agpn_chol.cuh"
+#include "agpn_eval.cuh"
+#include "agpn_predict.cuh"
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            char _b[512];                                                                       \
+            snprintf(_b, sizeof(_b), "CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(_e),   \
+                     cudaGetErrorString(_e), __FILE__, __LINE__, #expr);                        \
+            g_err = _b;                                                                         \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define USAGE_FAIL(msg)   \
+    do {                  \
+        g_err = (msg);    \
+        return 2;         \
+    } while (0)
+
+#define LAUNCH_CHECK()                  \
+    do {                                \
+        g_launches.fetch_add(1);        \
+        CUDA_TRY(cudaGetLastError());   \
+    } while (0)
+
+enum { PH_MEAN = 0, PH_ASM = 1, PH_DIAG = 2, PH_TRSM = 3, PH_SYRK = 4, PH_FINAL = 5, PH_COUNT = 6 };
+
+struct agpn_ctx {
+    int device = 0;
+    int N = 0, p = 0, q = 0, nblk = 0, npad = 0;
+    double* d_t = nullptr;
+    double* d_y = nullptr;
+    double* d_yerr = nullptr;
+    double tmean = 0.0, t0 = 0.0;
+    Structure S;
+    bool has_structure = false;
+    // batch workspace
+    size_t cap_mats = 0;
+    double* d_A = nullptr;
+    double* d_Linv = nullptr;
+    double* d_rhs = nullptr;
+    double* d_logdet = nullptr;
+    double* d_quad = nullptr;
+    int* d_info = nullptr;     // info | kflag | rflag, 3 * cap_mats
+    size_t cap_w = 0;
+    double* d_theta = nullptr;
+    double* d_out = nullptr;
+    int* d_status = nullptr;
+    size_t cap_D = 0;
+    // prediction workspace
+    size_t cap_linv_blocks = 0;
+    double* d_LinvAll = nullptr;
+    size_t cap_V = 0;
+    double* d_V = nullptr;
+    size_t cap_M = 0;
+    double* d_pred = nullptr;  // tstar | mstar | kss | mean | std, 5 * cap_M
+    // profiling
+    bool profiling = false;
+    double phase_ms[PH_COUNT] = {0, 0, 0, 0, 0, 0};
+    long long phase_launches[PH_COUNT] = {0, 0, 0, 0, 0, 0};
+    struct Ev { cudaEvent_t a, b; int ph; };
+    std::vector<Ev> evs;
+    bool attrs_set = false;
+};
+
+static double host_mean(const double* t, int n) {
+    long double s = 0.0L;
+    for (int i = 0; i < n; ++i) s += t[i];
+    return (double)(s / (long double)n);
+}
+
+extern "C" int agpn_version(void) { return 100; }
+extern "C" const char* agpn_last_error(void) { return g_err.c_str(); }
+extern "C" int agpn_kernel_npars(int family, int kind) { return kernel_npars(family, kind); }
+extern "C" int agpn_mean_npars(int kind) { return mean_npars(kind); }
+extern "C" long long agpn_launch_count(void) { return g_launches.load(); }
+
+static int set_kernel_attrs(agpn_ctx* c) {
+    if (c->attrs_set) return 0;
+    CUDA_TRY(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    c->attrs_set = true;
+    return 0;
+}
+
+extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, const double* time,
+                           const double* y, const double* yerr) {
+    if (!out || !time || !y || !yerr) USAGE_FAIL("agpn_create: null pointer");
+    if (N < 1 || p < 1 || p > AGPN_MAXP || q < 1 || q > AGPN_MAXQ)
+        USAGE_FAIL("agpn_create: need N >= 1, 1 <= p <= 8 series, 1 <= q <= 8 nodes");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) USAGE_FAIL("agpn_create: no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    agpn_ctx* c = new agpn_ctx();
+    c->device = device;
+    c->N = N;
+    c->p = p;
+    c->q = q;
+    c->nblk = (N + TB - 1) / TB;
+    c->npad = c->nblk * TB;
+    c->tmean = host_mean(time, N);
+    c->t0 = time[0];
+    memset(&c->S, 0, sizeof(Structure));
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_t, sizeof(double) * N)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_y, sizeof(double) * (size_t)N * p)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_yerr, sizeof(double) * (size_t)N * p)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_t, time, sizeof(double) * N, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_y, y, sizeof(double) * (size_t)N * p, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_yerr, yerr, sizeof(double) * (size_t)N * p, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        g_err = std::string("agpn_create: ") + cudaGetErrorString(e);
+        agpn_destroy(c);
+        return 1;
+    }
+    if (set_kernel_attrs(c)) {
+        agpn_destroy(c);
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int agpn_destroy(agpn_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    for (auto& e : c->evs) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    cudaFree(c->d_t); cudaFree(c->d_y); cudaFree(c->d_yerr);
+    cudaFree(c->d_A); cudaFree(c->d_Linv); cudaFree(c->d_rhs); cudaFree(c->d_logdet); cudaFree(c->d_quad);
+    cudaFree(c->d_info); cudaFree(c->d_theta); cudaFree(c->d_out); cudaFree(c->d_status);
+    cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred);
+    delete c;
+    return 0;
+}
+
+extern "C" int agpn_set_structure(agpn_ctx* c, const int* node_kind, const int* weight_kind,
+                                  const int* mean_nterms, const int* mean_kind, int use_means) {
+    if (!c || !node_kind || !weight_kind) USAGE_FAIL("agpn_set_structure: null pointer");
+    Structure S;
+    memset(&S, 0, sizeof(S));
+    S.p = c->p;
+    S.q = c->q;
+    S.use_means = use_means ? 1 : 0;
+    int off = 0;
+    for (int j = 0; j < c->q; ++j) {
+        const int n = kernel_npars(0, node_kind[j]);
+        if (n < 0) USAGE_FAIL("agpn_set_structure: unknown node kernel kind");
+        S.node_kind[j] = node_kind[j];
+        S.node_off[j] = off;
+        off += n;
+    }
+    for (int i = 0; i < c->p * c->q; ++i) {
+        const int n = kernel_npars(1, weight_kind[i]);
+        if (n < 0) USAGE_FAIL("agpn_set_structure: unknown weight kernel kind");
+        S.weight_kind[i] = weight_kind[i];
+        S.weight_off[i] = off;
+        off += n;
+    }
+    int nt = 0;
+    for (int i = 0; i < c->p; ++i) {
+        S.mean_first[i] = nt;
+        if (use_means) {
+            if (!mean_nterms) USAGE_FAIL("agpn_set_structure: mean_nterms is null");
+            for (int u = 0; u < mean_nterms[i]; ++u) {
+                if (nt >= AGPN_MAXTERMS) USAGE_FAIL("agpn_set_structure: more than 32 mean terms");
+                const int n = mean_npars(mean_kind[nt]);
+                if (n < 0) USAGE_FAIL("agpn_set_structure: unknown mean kind");
+                S.mean_kind[nt] = mean_kind[nt];
+                S.mean_off[nt] = off;
+                off += n;
+                ++nt;
+            }
+        }
+    }
+    S.mean_first[c->p] = nt;
+    S.jit_off = off;
+    off += c->p;
+    S.D = off;
+    c->S = S;
+    c->has_structure = true;
+    return 0;
+}
+
+extern "C" int agpn_theta_dim(const agpn_ctx* c) { return (c && c->has_structure) ? c->S.D : -1; }
+
+extern "C" int agpn_set_profiling(agpn_ctx* c, int enable) {
+    if (!c) USAGE_FAIL("agpn_set_profiling: null context");
+    c->profiling = enable != 0;
+    return 0;
+}
+
+extern "C" int agpn_phase_ms(agpn_ctx* c, double* ms6, long long* launches6) {
+    if (!c) USAGE_FAIL("agpn_phase_ms: null context");
+    for (int i = 0; i < PH_COUNT; ++i) {
+        if (ms6) ms6[i] = c->phase_ms[i];
+        if (launches6) launches6[i] = c->phase_launches[i];
+    }
+    return 0;
+}
+
+// ---- profiling helpers ---------------------------------------------------------------------
+struct PhaseScope {
+    agpn_ctx* c;
+    cudaStream_t st;
+    size_t idx;
+    bool on;
+    PhaseScope(agpn_ctx* c_, cudaStream_t st_, int ph, size_t& cursor) : c(c_), st(st_), idx(0), on(c_->profiling) {
+        c->phase_launches[ph] += 1;
+        if (!on) return;
+        if (cursor >= c->evs.size()) {
+            agpn_ctx::Ev e;
+            cudaEventCreate(&e.a);
+            cudaEventCreate(&e.b);
+            e.ph = ph;
+            c->evs.push_back(e);
+        }
+        idx = cursor++;
+        c->evs[idx].ph = ph;
+        cudaEventRecord(c->evs[idx].a, st);
+    }
+    ~PhaseScope() {
+        if (on) cudaEventRecord(c->evs[idx].b, st);
+    }
+};
+
+static void collect_phases(agpn_ctx* c, size_t used) {
+    if (!c->profiling) return;
+    for (size_t i = 0; i < used; ++i) {
+        float ms = 0.f;
+        cudaEventSynchronize(c->evs[i].b);
+        cudaEventElapsedTime(&ms, c->evs[i].a, c->evs[i].b);
+        c->phase_ms[c->evs[i].ph] += ms;
+    }
+}
+
+// ---- workspace -------------------------------------------------------------------------------
+static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
+    if (nmat > c->cap_mats) {
+        cudaFree(c->d_A); cudaFree(c->d_Linv); cudaFree(c->d_rhs); cudaFree(c->d_logdet); cudaFree(c->d_quad); cudaFree(c->d_info);
+        c->d_A = c->d_Linv = c->d_rhs = c->d_logdet = c->d_quad = nullptr;
+        c->d_info = nullptr;
+        c->cap_mats = 0;
+        const size_t np = (size_t)c->npad;
+        CUDA_TRY(cudaMalloc(&c->d_A, sizeof(double) * nmat * np * np));
+        CUDA_TRY(cudaMalloc(&c->d_Linv, sizeof(double) * nmat * TB * TB));
+        CUDA_TRY(cudaMalloc(&c->d_rhs, sizeof(double) * nmat * np));
+        CUDA_TRY(cudaMalloc(&c->d_logdet, sizeof(double) * nmat));
+        CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
+        CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 3 * nmat));
+        c->cap_mats = nmat;
+    }
+    if (W > c->cap_w || (size_t)c->S.D > c->cap_D) {
+        cudaFree(c->d_theta); cudaFree(c->d_out); cudaFree(c->d_status);
+        c->d_theta = c->d_out = nullptr;
+        c->d_status = nullptr;
+        c->cap_w = 0;
+        const size_t D = (size_t)c->S.D;
+        CUDA_TRY(cudaMalloc(&c->d_theta, sizeof(double) * W * D));
+        CUDA_TRY(cudaMalloc(&c->d_out, sizeof(double) * W));
+        CUDA_TRY(cudaMalloc(&c->d_status, sizeof(int) * W));
+        c->cap_w = W;
+        c->cap_D = D;
+    }
+    return 0;
+}
+
+// factorise nmat matrices in place (+ optional rhs), all on `st`
+static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor) {
+    size_t local_cursor = 0;
+    size_t& cur = cursor ? *cursor : local_cursor;
+    for (int k = 0; k < g.nblk; ++k) {
+        {
+            PhaseScope ps(c, st, PH_DIAG, cur);
+            potrf_diag_kernel<<<g.nmat, 256, POTRF_SMEM_BYTES, st>>>(g, k);
+            LAUNCH_CHECK();
+        }
+        const int nt = g.nblk - k - 1;
+        if (nt > 0) {
+            {
+                PhaseScope ps(c, st, PH_TRSM, cur);
+                trsm_kernel<<<dim3(nt, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
+                LAUNCH_CHECK();
+            }
+            {
+                PhaseScope ps(c, st, PH_SYRK, cur);
+                syrk_kernel<<<dim3(nt * (nt + 1) / 2, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
+                LAUNCH_CHECK();
+            }
+        }
+    }
+    return 0;
+}
+
+static int launch_assemble(agpn_ctx* c, AsmArgs& a, int W, cudaStream_t st) {
+    int tiles;
+    if (a.lower_only) {
+        const int nt = (a.rows_out + ASM_TILE - 1) / ASM_TILE;
+        tiles = nt * (nt + 1) / 2;
+    } else {
+        tiles = ((a.rows_out + ASM_TILE - 1) / ASM_TILE) * ((a.cols_out + ASM_TILE - 1) / ASM_TILE);
+    }
+    assemble_kernel<<<dim3(tiles, W), 256, 0, st>>>(c->S, a);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int theta_on_device,
+                                  double* out, int out_on_device, int* status, void* stream) {
+    if (!c || !theta || !out) USAGE_FAIL("agpn_loglike_batch: null pointer");
+    if (!c->has_structure) USAGE_FAIL("agpn_loglike_batch: call agpn_set_structure first");
+    if (W < 1) USAGE_FAIL("agpn_loglike_batch: W must be >= 1");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int p = c->p, D = c->S.D;
+    const size_t np = (size_t)c->npad;
+
+    // walkers per wave: bounded by free memory and by grid.y
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t have = c->cap_mats * np * np * sizeof(double);
+    const size_t per_walker = (size_t)p * (np * np + TB * TB + np) * sizeof(double) + 64;
+    size_t wave = (size_t)((free_b + have) * 0.85) / per_walker;
+    if (wave < 1) USAGE_FAIL("agpn_loglike_batch: not enough device memory for one walker");
+    if (wave > (size_t)W) wave = W;
+    if (wave * p > 65535) wave = 65535 / p;
+    if (ensure_batch_workspace(c, wave * p, wave)) return 1;
+
+    for (int ph = 0; ph < PH_COUNT; ++ph) {
+        c->phase_ms[ph] = 0;
+        c->phase_launches[ph] = 0;
+    }
+    const double half_n_log2pi = 0.5 * (double)c->N * std::log(2.0 * AGPN_PI);
+
+    for (size_t w0 = 0; w0 < (size_t)W; w0 += wave) {
+        const int Ww = (int)std::min(wave, (size_t)W - w0);
+        const int nmat = Ww * p;
+        size_t cur = 0;
+        const double* d_theta = theta + w0 * D;
+        if (!theta_on_device) {
+            CUDA_TRY(cudaMemcpyAsync(c->d_theta, theta + w0 * D, sizeof(double) * Ww * D, cudaMemcpyHostToDevice, st));
+            d_theta = c->d_theta;
+        }
+        CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double) * nmat, st));
+        CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double) * nmat, st));
+        CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 3 * c->cap_mats, st));
+        int* d_infoflag = c->d_info;
+        int* d_kflag = c->d_info + c->cap_mats;
+        int* d_rflag = c->d_info + 2 * c->cap_mats;
+        {
+            PhaseScope ps(c, st, PH_MEAN, cur);
+            MeanArgs m;
+            m.theta = d_theta; m.t = c->d_t; m.n = c->N; m.n_pad = c->npad; m.tmean = c->tmean; m.t0 = c->t0;
+            m.y = c->d_y; m.out = c->d_rhs; m.series0 = 0; m.nser = p; m.subtract = 1; m.rflag = d_rflag;
+            mean_kernel<<<dim3(p, Ww), 256, 0, st>>>(c->S, m);
+            LAUNCH_CHECK();
+        }
+        {
+            PhaseScope ps(c, st, PH_ASM, cur);
+            AsmArgs a;
+            a.theta = d_theta; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N;
+            a.rows_out = c->npad; a.cols_out = c->npad; a.yerr = c->d_yerr; a.out = c->d_A;
+            a.mat_stride = (long long)(np * np); a.ld = c->npad; a.series0 = 0; a.nser = p;
+            a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1;
+            a.use_trig = 1; a.vec2 = 1; a.torigin = c->t0; a.kflag = d_kflag;
+            if (launch_assemble(c, a, Ww, st)) return 1;
+        }
+        CholArgs g;
+        g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = nmat;
+        g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
+        g.info = d_infoflag;
+        if (run_cholesky(c, g, st, &cur)) return 1;
+        double* d_out = out_on_device ? out + w0 : c->d_out;
+        {
+            PhaseScope ps(c, st, PH_FINAL, cur);
+            finalize_kernel<<<(Ww + 127) / 128, 128, 0, st>>>(Ww, p, half_n_log2pi, c->d_quad, c->d_logdet, d_infoflag,
+                                                             d_kflag, d_rflag, d_out, c->d_status);
+            LAUNCH_CHECK();
+        }
+        if (!out_on_device)
+            CUDA_TRY(cudaMemcpyAsync(out + w0, c->d_out, sizeof(double) * Ww, cudaMemcpyDeviceToHost, st));
+        if (status) CUDA_TRY(cudaMemcpyAsync(status + w0, c->d_status, sizeof(int) * Ww, cudaMemcpyDeviceToHost, st));
+        const bool more = w0 + wave < (size_t)W;
+        if (!out_on_device || status || c->profiling || more) CUDA_TRY(cudaStreamSynchronize(st));
+        collect_phases(c, cur);
+    }
+    return 0;
+}
+
+extern "C" int agpn_covariance_block(agpn_ctx* c, const double* theta, int series, const double* ta, int na,
+                                     const double* tb, int nb, int square_quirk, int add_errors, double* out,
+                                     int out_on_device, void* stream) {
+    if (!c || !theta || !out) USAGE_FAIL("agpn_covariance_block: null pointer");
+    if (!c->has_structure) USAGE_FAIL("agpn_covariance_block: call agpn_set_structure first");
+    if (series < 0 || series >= c->p) USAGE_FAIL("agpn_covariance_block: series out of range");
+    if (!ta) na = c->N;
+    if (!tb) nb = c->N;
+    if (na < 1 || nb < 1) USAGE_FAIL("agpn_covariance_block: empty grid");
+    if (add_errors && (na != c->N || nb != c->N)) USAGE_FAIL("agpn_covariance_block: add_errors needs the training grid size");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double *d_th = nullptr, *d_ta = nullptr, *d_tb = nullptr, *d_out = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_th);
+        if (ta) cudaFree(d_ta);
+        if (tb) cudaFree(d_tb);
+        if (!out_on_device) cudaFree(d_out);
+    };
+#define CB_TRY(expr)                                                                   \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            g_err = std::string("agpn_covariance_block: ") + cudaGetErrorString(_e);   \
+            cleanup();                                                                 \
+            return 1;                                                                  \
+        }                                                                              \
+    } while (0)
+    CB_TRY(cudaMalloc(&d_th, sizeof(double) * c->S.D));
+    CB_TRY(cudaMemcpyAsync(d_th, theta, sizeof(double) * c->S.D, cudaMemcpyHostToDevice, st));
+    if (ta) {
+        CB_TRY(cudaMalloc(&d_ta, sizeof(double) * na));
+        CB_TRY(cudaMemcpyAsync(d_ta, ta, sizeof(double) * na, cudaMemcpyHostToDevice, st));
+    } else d_ta = c->d_t;
+    if (tb) {
+        CB_TRY(cudaMalloc(&d_tb, sizeof(double) * nb));
+        CB_TRY(cudaMemcpyAsync(d_tb, tb, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+    } else d_tb = c->d_t;
+    if (out_on_device) d_out = out;
+    else CB_TRY(cudaMalloc(&d_out, sizeof(double) * (size_t)na * nb));
+    AsmArgs a;
+    a.theta = d_th; a.ta = d_ta; a.tb = d_tb; a.na = na; a.nb = nb; a.rows_out = na; a.cols_out = nb;
+    a.yerr = c->d_yerr; a.out = d_out; a.mat_stride = (long long)na * nb; a.ld = nb; a.series0 = series; a.nser = 1;
+    a.lower_only = 0; a.square = square_quirk ? 1 : 0; a.add_err = add_errors ? 1 : 0; a.add_jit = 0;
+    a.pad_identity = 0; a.use_trig = 0; a.vec2 = ((nb % 2) == 0 && ((uintptr_t)d_out % 16) == 0) ? 1 : 0;
+    a.torigin = c->t0; a.kflag = nullptr;
+    rc = launch_assemble(c, a, 1, st);
+    if (rc == 0 && !out_on_device)
+        CB_TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)na * nb, cudaMemcpyDeviceToHost, st));
+    CB_TRY(cudaStreamSynchronize(st));
+    cleanup();
+#undef CB_TRY
+    return rc;
+}
+
+extern "C" int agpn_mean_table(agpn_ctx* c, const double* theta, const double* t, int n, double* out) {
+    if (!c || !theta || !out) USAGE_FAIL("agpn_mean_table: null pointer");
+    if (!c->has_structure) USAGE_FAIL("agpn_mean_table: call agpn_set_structure first");
+    if (!t) n = c->N;
+    if (n < 1) USAGE_FAIL("agpn_mean_table: empty grid");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double *d_th = nullptr, *d_t = nullptr, *d_o = nullptr;
+    CUDA_TRY(cudaMalloc(&d_th, sizeof(double) * c->S.D));
+    CUDA_TRY(cudaMalloc(&d_o, sizeof(double) * (size_t)c->p * n));
+    CUDA_TRY(cudaMemcpy(d_th, theta, sizeof(double) * c->S.D, cudaMemcpyHostToDevice));
+    MeanArgs m;
+    if (t) {
+        CUDA_TRY(cudaMalloc(&d_t, sizeof(double) * n));
+        CUDA_TRY(cudaMemcpy(d_t, t, sizeof(double) * n, cudaMemcpyHostToDevice));
+        m.t = d_t; m.tmean = host_mean(t, n); m.t0 = t[0];
+    } else {
+        m.t = c->d_t; m.tmean = c->tmean; m.t0 = c->t0;
+    }
+    m.theta = d_th; m.n = n; m.n_pad = n; m.y = nullptr; m.out = d_o; m.series0 = 0; m.nser = c->p; m.subtract = 0;
+    m.rflag = nullptr;
+    mean_kernel<<<dim3(c->p, 1), 256>>>(c->S, m);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpy(out, d_o, sizeof(double) * (size_t)c->p * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_th); cudaFree(d_o); cudaFree(d_t);
+    return 0;
+}
+
+extern "C" int agpn_predict(agpn_ctx* c, const double* theta, int series, int M, const double* tstar,
+                            double* mean_out, double* std_out, int* status, void* stream) {
+    if (!c || !theta || !tstar || !mean_out || !std_out) USAGE_FAIL("agpn_predict: null pointer");
+    if (!c->has_structure) USAGE_FAIL("agpn_predict: call agpn_set_structure first");
+    if (series < 0 || series >= c->p) USAGE_FAIL("agpn_predict: series out of range");
+    if (M < 1) USAGE_FAIL("agpn_predict: empty prediction grid");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t np = (size_t)c->npad;
+    if (ensure_batch_workspace(c, 1, 1)) return 1;
+    if ((size_t)c->nblk > c->cap_linv_blocks) {
+        cudaFree(c->d_LinvAll);
+        c->d_LinvAll = nullptr;
+        c->cap_linv_blocks = 0;
+        CUDA_TRY(cudaMalloc(&c->d_LinvAll, sizeof(double) * (size_t)c->nblk * TB * TB));
+        c->cap_linv_blocks = c->nblk;
+    }
+    const size_t Mpad = ((size_t)M + TB - 1) / TB * TB;
+    if (Mpad * np > c->cap_V) {
+        cudaFree(c->d_V);
+        c->d_V = nullptr;
+        c->cap_V = 0;
+        CUDA_TRY(cudaMalloc(&c->d_V, sizeof(double) * Mpad * np));
+        c->cap_V = Mpad * np;
+    }
+    if ((size_t)M > c->cap_M) {
+        cudaFree(c->d_pred);
+        c->d_pred = nullptr;
+        c->cap_M = 0;
+        CUDA_TRY(cudaMalloc(&c->d_pred, sizeof(double) * 5 * (size_t)M));
+        c->cap_M = M;
+    }
+    double* d_ts = c->d_pred;
+    double* d_ms = c->d_pred + c->cap_M;
+    double* d_kss = c->d_pred + 2 * c->cap_M;
+    double* d_mu = c->d_pred + 3 * c->cap_M;
+    double* d_sd = c->d_pred + 4 * c->cap_M;
+    CUDA_TRY(cudaMemcpyAsync(c->d_theta, theta, sizeof(double) * c->S.D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ts, tstar, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 3 * c->cap_mats, st));
+    int* d_kflag = c->d_info + c->cap_mats;
+    int* d_rflag = c->d_info + 2 * c->cap_mats;
+    // residual of the chosen series (arttwo.py:359-365)
+    MeanArgs m;
+    m.theta = c->d_theta; m.t = c->d_t; m.n = c->N; m.n_pad = c->npad; m.tmean = c->tmean; m.t0 = c->t0; m.y = c->d_y;
+    m.out = c->d_rhs; m.series0 = series; m.nser = 1; m.subtract = 1; m.rflag = d_rflag;
+    mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
+    LAUNCH_CHECK();
+    // mean on the prediction grid (arttwo.py:388): centred on / anchored at the prediction grid itself
+    m.t = d_ts; m.n = M; m.n_pad = M; m.tmean = host_mean(tstar, M); m.t0 = tstar[0]; m.y = nullptr; m.out = d_ms;
+    m.subtract = 0; m.rflag = nullptr;
+    mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
+    LAUNCH_CHECK();
+    // K + sigma^2 + s^2 (arttwo.py:367-370), factor (arttwo.py:371)
+    AsmArgs a;
+    a.theta = c->d_theta; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
+    a.yerr = c->d_yerr; a.out = c->d_A; a.mat_stride = (long long)(np * np); a.ld = c->npad; a.series0 = series; a.nser = 1;
+    a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1; a.use_trig = 1; a.vec2 = 1;
+    a.torigin = c->t0; a.kflag = d_kflag;
+    if (launch_assemble(c, a, 1, st)) return 1;
+    CholArgs g;
+    g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = 1;
+    g.Linv = c->d_LinvAll; g.linv_blocks = c->nblk; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
+    g.info = c->d_info;
+    if (run_cholesky(c, g, st, nullptr)) return 1;
+    kss_kernel<<<(M + 127) / 128, 128, 0, st>>>(c->S, c->d_theta, series, d_ts, M, d_kss);
+    LAUNCH_CHECK();
+    PredArgs pa;
+    pa.theta = c->d_theta; pa.tstar = d_ts; pa.ttrain = c->d_t; pa.M = M; pa.N = c->N; pa.n_pad = c->npad; pa.nblk = c->nblk;
+    pa.series = series; pa.square = (M == c->N) ? 1 : 0; pa.L = c->d_A; pa.ld = c->npad; pa.Linv = c->d_LinvAll;
+    pa.z = c->d_rhs; pa.V = c->d_V; pa.mstar = d_ms; pa.kss = d_kss; pa.mean_out = d_mu; pa.std_out = d_sd;
+    predict_kernel<<<(unsigned)(Mpad / TB), 256, GEMM_SMEM_BYTES, st>>>(c->S, pa);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(mean_out, d_mu, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(std_out, d_sd, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    int h_flags[3] = {0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(&h_flags[0], c->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&h_flags[1], d_kflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&h_flags[2], d_rflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (status) *status = h_flags[1] ? AGPN_STATUS_NOT_FINITE : (h_flags[0] ? AGPN_STATUS_NOT_PD : (h_flags[2] ? AGPN_STATUS_NOT_FINITE : AGPN_STATUS_OK));
+    return 0;
+}
+
+extern "C" int agpn_kernel_eval(int device, int family, int kind, const double* pars, const double* r,
+                                const double* t1, const double* t2, int rows, int cols, int square_quirk, double* out) {
+    if (!pars || !out) USAGE_FAIL("agpn_kernel_eval: null pointer");
+    if (kernel_npars(family, kind) < 0) USAGE_FAIL("agpn_kernel_eval: unknown kernel kind");
+    if (rows < 1 || cols < 1) USAGE_FAIL("agpn_kernel_eval: empty array");
+    const bool nonstat = (kind == K_LINEAR || kind == K_POLY);
+    if (nonstat && (!t1 || !t2)) USAGE_FAIL("agpn_kernel_eval: Linear / Polynomial need t1 and t2");
+    if (!nonstat && !r) USAGE_FAIL("agpn_kernel_eval: stationary kernels need r");
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t n = (size_t)rows * cols;
+    double *d_r = nullptr, *d_t1 = nullptr, *d_t2 = nullptr, *d_o = nullptr;
+    CUDA_TRY(cudaMalloc(&d_o, sizeof(double) * n));
+    if (r) {
+        CUDA_TRY(cudaMalloc(&d_r, sizeof(double) * n));
+        CUDA_TRY(cudaMemcpy(d_r, r, sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    if (t1) {
+        CUDA_TRY(cudaMalloc(&d_t1, sizeof(double) * rows));
+        CUDA_TRY(cudaMemcpy(d_t1, t1, sizeof(double) * rows, cudaMemcpyHostToDevice));
+    }
+    if (t2) {
+        CUDA_TRY(cudaMalloc(&d_t2, sizeof(double) * cols));
+        CUDA_TRY(cudaMemcpy(d_t2, t2, sizeof(double) * cols, cudaMemcpyHostToDevice));
+    }
+    const PKern k = prep_kernel(family, kind, pars);
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+    kernel_eval_kernel<<<blocks, 256>>>(k, d_r, d_t1, d_t2, rows, cols, square_quirk, d_o);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpy(out, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_r); cudaFree(d_t1); cudaFree(d_t2); cudaFree(d_o);
+    return 0;
+}
+
+extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, double* rhs, double* logdet,
+                                  double* quad, int* info, void* stream) {
+    if (!A || !logdet || !info) USAGE_FAIL("agpn_potrf_batched: null pointer");
+    if (rhs && !quad) USAGE_FAIL("agpn_potrf_batched: rhs needs quad");
+    if (n_pad < TB || n_pad % TB) USAGE_FAIL("agpn_potrf_batched: n_pad must be a positive multiple of 128");
+    if (nmat < 1 || nmat > 65535) USAGE_FAIL("agpn_potrf_batched: 1 <= nmat <= 65535");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    agpn_ctx tmp;
+    tmp.device = device;
+    if (set_kernel_attrs(&tmp)) return 1;
+    double* d_linv = nullptr;
+    CUDA_TRY(cudaMalloc(&d_linv, sizeof(double) * (size_t)nmat * TB * TB));
+    CUDA_TRY(cudaMemsetAsync(logdet, 0, sizeof(double) * nmat, st));
+    if (quad) CUDA_TRY(cudaMemsetAsync(quad, 0, sizeof(double) * nmat, st));
+    CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int) * nmat, st));
+    CholArgs g;
+    g.A = A; g.mat_stride = (long long)n_pad * n_pad; g.ld = n_pad; g.nblk = n_pad / TB; g.nmat = nmat; g.Linv = d_linv;
+    g.linv_blocks = 1; g.rhs = rhs; g.logdet = logdet; g.quad = quad; g.info = info;
+    int rc = run_cholesky(&tmp, g, st, nullptr);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_linv);
+    if (rc) return rc;
+    CUDA_TRY(e);
+    return 0;
+}

@@ -1,0 +1,282 @@
+// Covariance-block assembly and mean-residual kernels (sm_100a).
+//
+// assemble_kernel replaces the double loop of network.log_likelihood (arttwo.py:270-281),
+// network._covariance_matrix (arttwo.py:151-192) and the K* loop of network.prediction
+// (arttwo.py:373-384):   K_i = sum_j W_ij o F_j  (+ diag(sigma_i^2 + s_i^2)).
+// One CTA produces one 128 x 128 tile for ALL requested series of one walker: the node kernels
+// F_j do not depend on the series, so they are evaluated once per entry and reused (the
+// reference recomputes them p times, arttwo.py:277).  For the likelihood path only tiles on or
+// below the block diagonal are produced (the factorisation never reads the others).
+//
+// mean_kernel replaces network._mean / the residual y - m (arttwo.py:106-126, :262-264).
+#pragma once
+#include "agpn_eval.cuh"
+
+#define ASM_TILE 128
+#define ASM_NTRIG 4     // node kernels whose sin(pi r/P) term uses the angle-addition tables
+
+struct AsmArgs {
+    const double* theta;     // [W][D]
+    const double* ta;        // row grid  [na]
+    const double* tb;        // column grid [nb]
+    int na, nb;              // valid extents
+    int rows_out, cols_out;  // extents that may be written (>= na, nb when padded)
+    const double* yerr;      // [p][N] raw sigma or nullptr
+    double* out;             // matrices [(w * nser + s)] * mat_stride
+    long long mat_stride;
+    int ld;
+    int series0, nser;
+    int lower_only;          // tiles enumerated over the lower block triangle (square grids)
+    int square;              // WhiteNoise quirk: lag array is square
+    int add_err;             // + yerr^2 on the diagonal
+    int add_jit;             // + jitter^2 on the diagonal
+    int pad_identity;        // entries outside [na][nb]: 1 on the diagonal, else 0
+    int use_trig;            // angle-addition tables for node kernels with a sin term
+    int vec2;                // 16-byte stores allowed
+    double torigin;          // phase origin of the tables
+    int* kflag;              // [W * nser] set to 1 if a produced entry is not finite (or nullptr)
+};
+
+__global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ Structure S, const AsmArgs g) {
+    __shared__ PKern s_node[AGPN_MAXQ];
+    __shared__ PKern s_weight[AGPN_MAXP * AGPN_MAXQ];
+    __shared__ int s_slot[AGPN_MAXQ];
+    __shared__ double s_ta[ASM_TILE], s_tb[ASM_TILE];
+    __shared__ double s_diag[AGPN_MAXP][ASM_TILE];
+    __shared__ double s_trig[ASM_NTRIG][4][ASM_TILE];   // [slot][sin row, cos row, sin col, cos col]
+
+    const int tid = threadIdx.x;
+    const int w = blockIdx.y;
+    const int q = S.q;
+    int bi, bj;
+    if (g.lower_only) {
+        const int t = blockIdx.x;
+        bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        while (bi * (bi + 1) / 2 > t) --bi;
+        bj = t - bi * (bi + 1) / 2;
+    } else {
+        const int tcols = (g.cols_out + ASM_TILE - 1) / ASM_TILE;
+        bi = blockIdx.x / tcols;
+        bj = blockIdx.x % tcols;
+    }
+    const int i0 = bi * ASM_TILE, j0 = bj * ASM_TILE;
+    const double* th = g.theta + (size_t)w * S.D;
+
+    // ---- per-CTA preparation -------------------------------------------------------------------
+    if (tid < q) {
+        s_node[tid] = prep_kernel(0, S.node_kind[tid], th + S.node_off[tid]);
+    } else if (tid >= 32 && tid < 32 + g.nser * q) {
+        const int u = tid - 32;
+        const int s = u / q, j = u % q;
+        const int widx = j + q * (g.series0 + s);
+        s_weight[u] = prep_kernel(1, S.weight_kind[widx], th + S.weight_off[widx]);
+    }
+    if (tid == 64) {
+        int slot = 0;
+        for (int j = 0; j < AGPN_MAXQ; ++j) {
+            int v = -1;
+            if (j < q && g.use_trig && kernel_has_sin(S.node_kind[j]) && slot < ASM_NTRIG) v = slot++;
+            s_slot[j] = v;
+        }
+    }
+    if (tid < ASM_TILE) {
+        const int gi = i0 + tid;
+        s_ta[tid] = g.ta[gi < g.na ? gi : g.na - 1];
+    } else {
+        const int gj = j0 + tid - ASM_TILE;
+        s_tb[tid - ASM_TILE] = g.tb[gj < g.nb ? gj : g.nb - 1];
+    }
+    if (bi == bj && (g.add_err || g.add_jit)) {
+        for (int u = tid; u < g.nser * ASM_TILE; u += 256) {
+            const int s = u / ASM_TILE, r = u % ASM_TILE;
+            const int gi = i0 + r;
+            double v = 0.0;
+            if (gi < g.na) {
+                if (g.add_err) {
+                    const double e = g.yerr[(size_t)(g.series0 + s) * g.na + gi];
+                    v += e * e;
+                }
+                if (g.add_jit) {
+                    const double jt = th[S.jit_off + g.series0 + s];
+                    v += jt * jt;
+                }
+            }
+            s_diag[s][r] = v;
+        }
+    }
+    __syncthreads();
+    if (g.use_trig) {
+        for (int j = 0; j < q; ++j) {
+            const int slot = s_slot[j];
+            if (slot < 0) continue;
+            const double b = s_node[j].b;
+            double sv, cv;
+            if (tid < ASM_TILE) {
+                sincos(b * (s_ta[tid] - g.torigin), &sv, &cv);
+                s_trig[slot][0][tid] = sv;
+                s_trig[slot][1][tid] = cv;
+            } else {
+                sincos(b * (s_tb[tid - ASM_TILE] - g.torigin), &sv, &cv);
+                s_trig[slot][2][tid - ASM_TILE] = sv;
+                s_trig[slot][3][tid - ASM_TILE] = cv;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- entries ---------------------------------------------------------------------------------
+    const int tx = tid & 63, ty = tid >> 6;
+    const int c0 = 2 * tx;
+    const double tb0 = s_tb[c0], tb1 = s_tb[c0 + 1];
+    const int gj0 = j0 + c0;
+    unsigned bad = 0;
+    for (int rr = 0; rr < ASM_TILE / 4; ++rr) {
+        const int row = ty + 4 * rr;
+        const int gi = i0 + row;
+        if (gi >= g.rows_out) break;
+        const double t1 = s_ta[row];
+        const double r0 = t1 - tb0, r1 = t1 - tb1;
+        const bool dg0 = g.square && (gi == gj0), dg1 = g.square && (gi == gj0 + 1);
+        double F0[AGPN_MAXQ], F1[AGPN_MAXQ];
+#pragma unroll
+        for (int j = 0; j < AGPN_MAXQ; ++j) {
+            if (j < q) {
+                const PKern& kn = s_node[j];
+                const int slot = s_slot[j];
+                if (slot >= 0) {
+                    const double sr = s_trig[slot][0][row], cr = s_trig[slot][1][row];
+                    const double sa = sr * s_trig[slot][3][c0] - cr * s_trig[slot][2][c0];
+                    const double sb = sr * s_trig[slot][3][c0 + 1] - cr * s_trig[slot][2][c0 + 1];
+                    F0[j] = kn.amp * kern_shape_with_sin(kn, r0, sa);
+                    F1[j] = kn.amp * kern_shape_with_sin(kn, r1, sb);
+                } else if (kn.kind == K_CONSTANT) {
+                    F0[j] = F1[j] = kn.amp;
+                } else {
+                    F0[j] = kn.amp * kern_shape(kn, r0, t1, tb0, dg0);
+                    F1[j] = kn.amp * kern_shape(kn, r1, t1, tb1, dg1);
+                }
+            } else {
+                F0[j] = F1[j] = 0.0;
+            }
+        }
+        for (int s = 0; s < g.nser; ++s) {
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < AGPN_MAXQ; ++j) {
+                if (j < q) {
+                    const PKern& kw = s_weight[s * q + j];
+                    if (kw.kind == K_CONSTANT) {
+                        v0 = fma(kw.amp, F0[j], v0);
+                        v1 = fma(kw.amp, F1[j], v1);
+                    } else {
+                        v0 = fma(kw.amp * kern_shape(kw, r0, t1, tb0, dg0), F0[j], v0);
+                        v1 = fma(kw.amp * kern_shape(kw, r1, t1, tb1, dg1), F1[j], v1);
+                    }
+                }
+            }
+            if (bi == bj && (g.add_err || g.add_jit)) {
+                if (gi == gj0) v0 += s_diag[s][row];
+                if (gi == gj0 + 1) v1 += s_diag[s][row];
+            }
+            const bool in0 = (gi < g.na) && (gj0 < g.nb), in1 = (gi < g.na) && (gj0 + 1 < g.nb);
+            if (!in0) v0 = (g.pad_identity && gi == gj0) ? 1.0 : 0.0;
+            if (!in1) v1 = (g.pad_identity && gi == gj0 + 1) ? 1.0 : 0.0;
+            if (!isfinite(v0) || !isfinite(v1)) bad |= 1u << s;
+            double* dst = g.out + (size_t)((size_t)w * g.nser + s) * g.mat_stride + (size_t)gi * g.ld + gj0;
+            if (g.vec2 && gj0 + 1 < g.cols_out) {
+                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            } else {
+                if (gj0 < g.cols_out) dst[0] = v0;
+                if (gj0 + 1 < g.cols_out) dst[1] = v1;
+            }
+        }
+    }
+    if (bad && g.kflag != nullptr) {
+        for (int s = 0; s < g.nser; ++s)
+            if (bad & (1u << s)) g.kflag[(size_t)w * g.nser + s] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct MeanArgs {
+    const double* theta;   // [W][D]
+    const double* t;       // [n]
+    int n, n_pad;
+    double tmean, t0;
+    const double* y;       // [p][n] (subtract mode) or nullptr
+    double* out;           // [(w * nser + s)][n_pad]
+    int series0, nser;
+    int subtract;          // 1: out = y - m ; 0: out = m
+    int* rflag;            // [W * nser] non-finite residual flag (or nullptr)
+};
+
+// grid (nser, W), 256 threads
+__global__ void __launch_bounds__(256) mean_kernel(const __grid_constant__ Structure S, const MeanArgs g) {
+    __shared__ int s_halley[AGPN_MAXTERMS];
+    const int s = blockIdx.x, w = blockIdx.y;
+    const int series = g.series0 + s;
+    const double* th = g.theta + (size_t)w * S.D;
+    const int first = S.use_means ? S.mean_first[series] : 0;
+    const int last = S.use_means ? S.mean_first[series + 1] : 0;
+    const int tid = threadIdx.x;
+    for (int tt = first; tt < last; ++tt) {
+        int any = 0;
+        if (S.mean_kind[tt] == M_KEPLERIAN) {
+            int local = 0;
+            for (int n = tid; n < g.n; n += 256) {
+                double E0;
+                const double M1 = kepler_m1(th + S.mean_off[tt], g.t[n], g.t0, &E0);
+                local |= (fabs(M1) > 1e-10) ? 1 : 0;
+            }
+            any = __syncthreads_or(local);
+        }
+        if (tid == 0) s_halley[tt - first] = any;
+    }
+    __syncthreads();
+    double* out = g.out + ((size_t)w * g.nser + s) * g.n_pad;
+    int bad = 0;
+    for (int n = tid; n < g.n_pad; n += 256) {
+        double v = 0.0;
+        if (n < g.n) {
+            const double t = g.t[n];
+            double m = 0.0;
+            for (int tt = first; tt < last; ++tt)
+                m += mean_term(S.mean_kind[tt], th + S.mean_off[tt], t, g.tmean, g.t0, s_halley[tt - first] != 0);
+            v = g.subtract ? (g.y[(size_t)series * g.n + n] - m) : m;
+            if (!isfinite(v)) bad = 1;
+        }
+        out[n] = v;
+    }
+    if (bad && g.rflag != nullptr) g.rflag[(size_t)w * g.nser + s] = 1;
+}
+
+// element-wise value of one kernel object (node.py / weight.py __call__)
+__global__ void kernel_eval_kernel(PKern k, const double* r, const double* t1, const double* t2,
+                                   int rows, int cols, int square, double* out) {
+    const size_t n = (size_t)rows * cols;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / cols), j = (int)(idx % cols);
+        const double rv = r ? r[idx] : 0.0;
+        const double a = t1 ? t1[i] : 0.0, b = t2 ? t2[j] : 0.0;
+        out[idx] = k.amp * kern_shape(k, rv, a, b, square && i == j);
+    }
+}
+
+// per-walker reduction of the per-(walker, series) pieces -> log-likelihood (arttwo.py:285-290)
+__global__ void finalize_kernel(int W, int p, double half_n_log2pi, const double* quad, const double* logdet,
+                                const int* info, const int* kflag, const int* rflag, double* out, int* status) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    double ll = 0.0;
+    int st = 0;
+    for (int s = 0; s < p; ++s) {
+        const int m = w * p + s;
+        if (kflag[m]) { st = 2; break; }      // cho_factor check_finite -> ValueError
+        if (info[m]) { st = 1; break; }       // LinAlgError -> -inf (arttwo.py:288-289)
+        if (rflag[m]) { st = 2; break; }      // cho_solve check_finite on the residual
+        ll += -0.5 * quad[m] - logdet[m] - half_n_log2pi;
+    }
+    out[w] = st == 0 ? ll : (st == 1 ? -INFINITY : NAN);
+    status[w] = st;
+}

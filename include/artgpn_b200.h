@@ -1,0 +1,149 @@
+/*
+ * artgpn_b200 -- C ABI of the B200-native likelihood / prediction hot path of artgpn.
+ *
+ * The reference (jdavidrcamacho/artgpn) has no FFI layer: its boundary is the Python class
+ * artgpn.arttwo.network plus the node / weight / mean classes.  Every entry point below names
+ * the reference code it replaces (file:line relative to the reference tree).  The Python
+ * package artgpn_b200 binds these with ctypes (artgpn_b200/_lib.py); INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types (streams travel as void*).
+ *   - every function returns 0 on success, non-zero on CUDA / usage errors; the message is
+ *     available from agpn_last_error().  Numerical failure of a walker is NOT an error return:
+ *     it is reported through out[w] / status[w] (see agpn_loglike_batch).
+ *   - all floating point data is IEEE binary64, row-major.
+ *   - one context per (process, device); calls on one context are serialised by the caller.
+ *
+ * Kernel kind ids (node.py / weight.py class -> id; Laplacian shares Exponential's formula,
+ * weight.py:573-574 vs :618-619):
+ *   0 Constant  1 WhiteNoise  2 SquaredExponential  3 Periodic  4 QuasiPeriodic
+ *   5 RationalQuadratic  6 RQP  7 Cosine  8 Exponential|Laplacian  9 Matern32  10 Matern52
+ *   11 Linear  12 GammaExp  13 Polynomial
+ * Node kernels take their .pars as in node.py (1..4 doubles); weight kernels take the same
+ * list with the amplitude `weight` first (weight.py), except Constant / WhiteNoise (1 double).
+ * Mean kind ids (mean.py): 0 Constant 1 Linear 2 Parabola 3 Cubic 4 Sine 5 Cosine 6 Keplerian;
+ * a mean.Sum is a list of terms.
+ *
+ * theta row layout (D = agpn_theta_dim doubles), SURVEY.md section 8(b):
+ *   node_0.pars .. node_{q-1}.pars | weight_0.pars .. weight_{pq-1}.pars (list index j + q*i,
+ *   arttwo.py:274) | mean terms of series 0 .. p-1 in order | jitter_0 .. jitter_{p-1}
+ */
+#ifndef ARTGPN_B200_H
+#define ARTGPN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agpn_ctx agpn_ctx;
+
+#define AGPN_FAMILY_NODE 0
+#define AGPN_FAMILY_WEIGHT 1
+
+/* per-walker status values written by agpn_loglike_batch */
+#define AGPN_STATUS_OK 0
+#define AGPN_STATUS_NOT_PD 1      /* scipy LinAlgError -> reference returns -inf (arttwo.py:288-289) */
+#define AGPN_STATUS_NOT_FINITE 2  /* scipy check_finite ValueError (arttwo.py:284) */
+
+int agpn_version(void);
+
+/* Last error message of this thread's most recent failing call ("" if none). */
+const char* agpn_last_error(void);
+
+/* Number of .pars doubles of a kernel / mean kind; -1 if the id is unknown. */
+int agpn_kernel_npars(int family, int kind);
+int agpn_mean_npars(int kind);
+
+/*
+ * Replaces network.__init__ (arttwo.py:27-51): packs time[N], y[p][N] and the RAW sigma
+ * yerr[p][N] (not squared, arttwo.py:40-48) and copies them to `device` once.
+ */
+int agpn_create(agpn_ctx** out, int device, int N, int p, int q,
+                const double* time, const double* y, const double* yerr);
+int agpn_destroy(agpn_ctx* ctx);
+
+/*
+ * Fixes which kernel / mean classes the parameter rows refer to (the reference re-reads
+ * type(k) and k.pars on every call, arttwo.py:273-277).
+ *   node_kind[q]; weight_kind[p*q] in list order j + q*i; mean_nterms[p] (0 == None,
+ *   arttwo.py:112-113); mean_kind[sum(mean_nterms)].
+ *   use_means == 0 reproduces `if means` being falsy (arttwo.py:263): nothing is subtracted
+ *   and the theta row carries no mean parameters.
+ */
+int agpn_set_structure(agpn_ctx* ctx, const int* node_kind, const int* weight_kind,
+                       const int* mean_nterms, const int* mean_kind, int use_means);
+int agpn_theta_dim(const agpn_ctx* ctx);
+
+/*
+ * Replaces network.log_likelihood (arttwo.py:240-290) for W parameter rows at once.
+ *   theta[W][D], out[W]; *_on_device says whether the pointer is device memory on ctx's device
+ *   (else host memory: the copy happens inside the call on `stream`).
+ *   status (host, may be NULL) receives AGPN_STATUS_* per walker.  out[w] is -inf for
+ *   NOT_PD and NaN for NOT_FINITE.  The call returns after the results are in `out`
+ *   (host out) or are stream-ordered on `stream` (device out, status == NULL).
+ */
+int agpn_loglike_batch(agpn_ctx* ctx, int W, const double* theta, int theta_on_device,
+                       double* out, int out_on_device, int* status, void* stream);
+
+/*
+ * Replaces network._covariance_matrix (arttwo.py:151-192) and the K* loop of prediction
+ * (arttwo.py:373-384): out[na][nb] = sum_j W_{series,j}(ta,tb) * F_j(ta,tb) for one theta row.
+ *   ta == NULL / tb == NULL mean the training grid.  `square_quirk` != 0 makes WhiteNoise put
+ *   wn^2 where row index == column index (node.py:68-72 fires whenever the lag array is square).
+ *   add_errors != 0 adds yerr[series]^2 on the diagonal (needs na == nb == N, arttwo.py:190-191).
+ *   series is 0-based.  theta, ta, tb: host.  out: host or device.
+ */
+int agpn_covariance_block(agpn_ctx* ctx, const double* theta, int series,
+                          const double* ta, int na, const double* tb, int nb,
+                          int square_quirk, int add_errors,
+                          double* out, int out_on_device, void* stream);
+
+/*
+ * Replaces network._mean (arttwo.py:106-126): out[p][n] on the grid t (NULL = training grid).
+ * Rows of series without a mean stay 0.  theta: full host row.  out: host.
+ */
+int agpn_mean_table(agpn_ctx* ctx, const double* theta, const double* t, int n, double* out);
+
+/*
+ * Replaces network.prediction (arttwo.py:329-396) for one theta row and one series (0-based):
+ * mean_out[M] = K* K^-1 r + m(t*), std_out[M] = sqrt(diag(K** + s^2 I - K* K^-1 K*^T)).
+ * All pointers host.  *status receives AGPN_STATUS_* of the factorisation (the reference lets
+ * LinAlgError escape here, arttwo.py:371).
+ */
+int agpn_predict(agpn_ctx* ctx, const double* theta, int series, int M, const double* tstar,
+                 double* mean_out, double* std_out, int* status, void* stream);
+
+/*
+ * Replaces one kernel object's __call__ (node.py / weight.py): element-wise value on a
+ * [rows][cols] lag array r, or on t1[rows] x t2[cols] for Linear / Polynomial (r ignored).
+ * Host pointers; runs on `device`.  square_quirk as above (1 iff rows == cols in the reference).
+ */
+int agpn_kernel_eval(int device, int family, int kind, const double* pars,
+                     const double* r, const double* t1, const double* t2,
+                     int rows, int cols, int square_quirk, double* out);
+
+/*
+ * Device-side building blocks, exported for tests / profiling of the Cholesky path alone:
+ * in-place batched factorisation of nmat row-major [n_pad][n_pad] matrices already resident on
+ * the device (lower triangle referenced; n_pad multiple of 128), optional right-hand sides
+ * rhs[nmat][n_pad] overwritten with L^-1 rhs.  logdet[nmat] = sum log L_kk, quad[nmat] =
+ * |L^-1 rhs|^2, info[nmat] = 0 / 1 (not PD).  All pointers device.
+ */
+int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, double* rhs,
+                       double* logdet, double* quad, int* info, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+long long agpn_launch_count(void);
+
+/* Last-call timing probe: device milliseconds spent per phase of the last
+ * agpn_loglike_batch when profiling was enabled with agpn_set_profiling(ctx, 1).
+ * phases: 0 mean residual, 1 assembly, 2 diagonal-block factor, 3 panel solve,
+ * 4 trailing update, 5 finalise.  Returns 0 if unavailable. */
+int agpn_set_profiling(agpn_ctx* ctx, int enable);
+int agpn_phase_ms(agpn_ctx* ctx, double* ms6, long long* launches6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARTGPN_B200_H */
