@@ -1,0 +1,63 @@
+"""GPU: BASELINE.json sizes (3 x 2048, 2 nodes) -- one oracle evaluation plus size-independent
+properties (walker-order invariance, batch-composition invariance, jitter monotonicity)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c3():
+    from artgpn_b200 import synth, node, weight, mean
+    from artgpn_b200.arttwo import network
+    t, y, sig = synth.make_data(2048, 3, seed=0)
+    theta = synth.make_walkers(12, p=3, q=2, weights="Constant", seed=1)
+    net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+    o = synth.objects_from_row(node, weight, mean, theta[0], 3, 2, "Constant")
+    net.set_structure(*o[:3])
+    return net, (t, y, sig), theta
+
+
+def test_c3_one_walker_vs_oracle(c3):
+    from artgpn_b200 import synth
+    net, (t, y, sig), theta = c3
+
+    class M(object):
+        def __getattr__(self, name):
+            return lambda *pars: (name, list(pars))
+    m = M()
+    o = synth.objects_from_row(m, m, m, theta[0], 3, 2, "Constant")
+    exp = oracle.log_likelihood(t, y, sig, 2, *o)
+    got = net.log_likelihood_batch(theta[:1])[0]
+    assert abs(got - exp) <= 1e-9 * abs(exp), (got, exp)
+
+
+def test_c3_batch_invariances(c3):
+    net, _, theta = c3
+    full = net.log_likelihood_batch(theta)
+    assert np.all(np.isfinite(full))
+    perm = np.random.default_rng(0).permutation(theta.shape[0])
+    assert np.array_equal(net.log_likelihood_batch(theta[perm].copy()), full[perm])      # order
+    assert np.array_equal(net.log_likelihood_batch(theta[3:7].copy()), full[3:7])         # composition
+    again = net.log_likelihood_batch(theta)
+    assert np.array_equal(again, full)                                                   # run-to-run
+
+
+def test_c3_se_weights_one_walker_vs_oracle():
+    from artgpn_b200 import synth, node, weight, mean
+    from artgpn_b200.arttwo import network
+    t, y, sig = synth.make_data(1024, 3, seed=0)
+    theta = synth.make_walkers(2, p=3, q=2, weights="SquaredExponential", seed=1)
+    net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+    o = synth.objects_from_row(node, weight, mean, theta[1], 3, 2, "SquaredExponential")
+    got = net.log_likelihood(*o)
+
+    class M(object):
+        def __getattr__(self, name):
+            return lambda *pars: (name, list(pars))
+    m = M()
+    exp = oracle.log_likelihood(t, y, sig, 2, *synth.objects_from_row(m, m, m, theta[1], 3, 2, "SquaredExponential"))
+    assert abs(got - exp) <= 1e-9 * abs(exp), (got, exp)

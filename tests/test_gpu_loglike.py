@@ -1,0 +1,124 @@
+"""GPU parity tests proper: log_likelihood through the C ABI vs the reference goldens and vs the
+oracle on seeded inputs.  Tolerance: 1e-9 relative (north_star); observed ~1e-13."""
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import oracle
+
+pytestmark = pytest.mark.gpu
+LL_RTOL = 1e-9
+
+
+@pytest.mark.parametrize("case", H.cases()["loglike"], ids=lambda c: c["name"])
+def test_loglike_vs_reference_goldens(case):
+    net = H.product_network(case)
+    nodes, weights, means = H.product_objs(case)
+    exp = case["ll"]
+    if exp == "ValueError":
+        with pytest.raises(ValueError):
+            net.log_likelihood(nodes, weights, means, case["jitters"])
+    elif exp == "-inf":
+        assert np.isneginf(net.log_likelihood(nodes, weights, means, case["jitters"]))
+    else:
+        got = net.log_likelihood(nodes, weights, means, case["jitters"])
+        assert abs(got - exp) <= LL_RTOL * abs(exp), (got, exp, abs(got - exp) / abs(exp))
+
+
+@pytest.mark.parametrize("b", H.cases()["batch"], ids=lambda c: c["name"])
+def test_batch_vs_reference_goldens(b):
+    from artgpn_b200 import synth, node, weight, mean
+    a = H.arrays()
+    theta, exp = a[b["name"] + "_theta"], a[b["name"] + "_ll"]
+    net = H.product_network(b["data"], b["q"])
+    nodes, ws, ms, jit = synth.objects_from_row(node, weight, mean, theta[0], b["p"], b["q"], b["weights"])
+    s = net.set_structure(nodes, ws, ms)
+    assert s.D == theta.shape[1]
+    assert np.array_equal(s.pack(nodes, ws, ms, jit), theta[0])
+    got, status = net.log_likelihood_batch(theta, return_status=True)
+    assert np.all(status == 0)
+    assert H.rel_err(got, exp) <= LL_RTOL, (got, exp)
+    # single-row calls give bit-identical values to the batched call, in any order
+    got_rev = net.log_likelihood_batch(theta[::-1].copy())
+    assert np.array_equal(got_rev[::-1], got)
+    one = net.log_likelihood(nodes, ws, ms, jit)
+    assert one == got[0]
+
+
+@pytest.mark.parametrize("N", [1, 2, 20, 127, 128, 129, 255, 256, 300])
+def test_ragged_sizes_vs_oracle(N):
+    from artgpn_b200 import synth, node, weight, mean
+    from artgpn_b200.arttwo import network
+    t, y, sig = synth.make_data(N, 2, seed=10 + N)
+    theta = synth.make_walkers(3, p=2, q=2, weights="SquaredExponential", seed=3)
+    net = network(2, t, y[0], sig[0], y[1], sig[1])
+    nodes, ws, ms, jit = synth.objects_from_row(node, weight, mean, theta[0], 2, 2, "SquaredExponential")
+    net.set_structure(nodes, ws, ms)
+    got = net.log_likelihood_batch(theta)
+
+    class M(object):
+        def __getattr__(self, name):
+            return lambda *pars: (name, list(pars))
+    m = M()
+    for w in range(3):
+        o = synth.objects_from_row(m, m, m, theta[w], 2, 2, "SquaredExponential")
+        exp = oracle.log_likelihood(t, y, sig, 2, *o)
+        assert abs(got[w] - exp) <= LL_RTOL * abs(exp), (N, w, got[w], exp)
+
+
+def test_batch_status_and_mixed_failures():
+    """-inf / NaN rows inside a batch do not disturb their neighbours (arttwo.py:288-289)."""
+    from artgpn_b200 import synth, node, weight, mean
+    b = H.cases()["batch"][0]
+    a = H.arrays()
+    theta = a[b["name"] + "_theta"].copy()
+    exp = a[b["name"] + "_ll"]
+    net = H.product_network(b["data"], b["q"])
+    nodes, ws, ms, jit = synth.objects_from_row(node, weight, mean, theta[0], b["p"], b["q"], b["weights"])
+    net.set_structure(nodes, ws, ms)
+    theta[1, 0] = np.nan            # NaN hyper-parameter -> status 2
+    theta[3, 1] = 0.0               # period 0 -> division by zero -> NaN in K -> status 2
+    got, status = net.log_likelihood_batch(theta, return_status=True)
+    assert list(status) == [0, 2, 0, 2, 0, 0]
+    assert np.isnan(got[1]) and np.isnan(got[3])
+    keep = [0, 2, 4, 5]
+    assert H.rel_err(got[keep], exp[keep]) <= LL_RTOL
+
+
+def test_jitter_sign_insensitive_and_pars_is_source_of_truth():
+    case = H.loglike_case("G4_sun50_initial")
+    net = H.product_network(case)
+    nodes, weights, means = H.product_objs(case)
+    base = net.log_likelihood(nodes, weights, means, case["jitters"])
+    neg = net.log_likelihood(nodes, weights, means, [-j for j in case["jitters"]])
+    assert base == neg
+    nodes[0].pars[0] = 15.0          # attribute .ell_e stays 10: only .pars counts (arttwo.py:273)
+    changed = net.log_likelihood(nodes, weights, means, case["jitters"])
+    ref = dict(case)
+    ref["nodes"] = [["QuasiPeriodic", [15.0, 20.0, 0.5]]]
+    exp = H.oracle_loglike(ref)
+    assert abs(changed - exp) <= LL_RTOL * abs(exp)
+
+
+def test_too_few_weights_is_index_error():
+    case = H.loglike_case("G4_sun50_initial")
+    net = H.product_network(case)
+    nodes, weights, means = H.product_objs(case)
+    with pytest.raises(IndexError):
+        net.log_likelihood(nodes, weights[:2], means, case["jitters"])
+
+
+def test_torch_device_tensor_path():
+    import torch
+    from artgpn_b200 import synth, node, weight, mean
+    b = H.cases()["batch"][2]
+    a = H.arrays()
+    theta, exp = a[b["name"] + "_theta"], a[b["name"] + "_ll"]
+    net = H.product_network(b["data"], b["q"])
+    nodes, ws, ms, jit = synth.objects_from_row(node, weight, mean, theta[0], b["p"], b["q"], b["weights"])
+    net.set_structure(nodes, ws, ms)
+    th = torch.from_numpy(theta).cuda()
+    out = net.log_likelihood_batch(th)
+    torch.cuda.synchronize()
+    assert out.is_cuda and H.rel_err(out.cpu().numpy(), exp) <= LL_RTOL
+    assert np.array_equal(out.cpu().numpy(), net.log_likelihood_batch(theta))
