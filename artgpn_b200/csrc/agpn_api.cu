@@ -638,3 +638,52 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     CUDA_TRY(e);
     return 0;
 }
+
+// ---- FP64 tensor-pipe peak probe (roofline denominator measured in the same run) -------------
+template <int NACC>
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double acc[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i][0] = acc[i][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += acc[i][0] + acc[i][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int agpn_dmma_peak(int device, double* tflops) {
+    if (!tflops) USAGE_FAIL("agpn_dmma_peak: null pointer");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 2, threads = 256, iters = 20000;
+    constexpr int NACC = 8;
+    double* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, sizeof(double) * grid * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    dmma_peak_kernel<NACC><<<grid, threads>>>(out, 1000);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        dmma_peak_kernel<NACC><<<grid, threads>>>(out, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 256.0 * NACC * (double)iters * (threads / 32) * grid;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return 0;
+}

@@ -1,0 +1,64 @@
+"""Walker sharding over the GPUs of one box.
+
+Walkers (parameter rows) are independent -- the reference evaluates them in separate processes
+(examples/Sun/01_emcee.py:119-122) -- so a batch is block-partitioned over the ranks of a
+``torch.distributed`` group, each rank evaluates its rows on its own GPU, and ONE collective
+gathers the per-walker log-likelihoods (NCCL on GPUs; the same code runs on gloo / CPU tensors
+in the tests with an injected evaluator).  No matrix is ever split across GPUs and sharding does
+not change any value: every rank produces bit-identical numbers to a single-GPU run.
+"""
+import numpy as np
+
+
+def shard_bounds(W, world_size, rank):
+    """[lo, hi) rows of rank `rank`: contiguous blocks, the first W % world_size ranks get one more."""
+    base, rem = divmod(int(W), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(W, world_size):
+    return [shard_bounds(W, world_size, r)[1] - shard_bounds(W, world_size, r)[0] for r in range(world_size)]
+
+
+def gather_loglikes(local, W, group=None):
+    """All-gather the per-rank result slices (1-D float64 torch tensors, sizes = shard_sizes) into the
+    full [W] vector on every rank.  One collective; uneven shards are padded to the largest."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(W, world)
+    mx = max(sizes)
+    if local.numel() != sizes[dist.get_rank(group)]:
+        raise ValueError("local slice has %d rows, expected %d" % (local.numel(), sizes[dist.get_rank(group)]))
+    if min(sizes) == mx:
+        out = torch.empty(W, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    pad = torch.full((mx,), float("nan"), dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local
+    buf = torch.empty(mx * world, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    return torch.cat([buf[r * mx:r * mx + sizes[r]] for r in range(world)])
+
+
+def log_likelihood_batch_sharded(net, theta, group=None, evaluator=None):
+    """Log-likelihoods of all W rows of `theta` (same full array on every rank), computed
+    W / world_size rows per rank and gathered.  `evaluator(theta_slice) -> 1-D float64 torch tensor`
+    defaults to ``net.log_likelihood_batch`` on this rank's GPU."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    W = theta.shape[0]
+    lo, hi = shard_bounds(W, world, rank)
+    mine = theta[lo:hi]
+    if evaluator is None:
+        if hi > lo:
+            if not torch.is_tensor(mine):
+                mine = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float64)).cuda(net._device)
+            local = net.log_likelihood_batch(mine)
+        else:
+            local = torch.empty(0, dtype=torch.float64, device="cuda:%d" % net._device)
+    else:
+        local = evaluator(mine)
+    return gather_loglikes(local, W, group)

@@ -133,6 +133,10 @@ int agpn_kernel_eval(int device, int family, int kind, const double* pars,
 int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, double* rhs,
                        double* logdet, double* quad, int* info, void* stream);
 
+/* Measured issue-rate peak of the FP64 tensor instruction (DMMA.8x8x4) on `device`, in TFLOP/s:
+ * the denominator bench.py uses for the Cholesky roofline (MEASURED_PEAKS.json has no FP64 figure). */
+int agpn_dmma_peak(int device, double* tflops);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 long long agpn_launch_count(void);
 
