@@ -307,7 +307,7 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
             }
             {
                 PhaseScope ps(c, st, PH_SYRK, cur);
-                syrk_kernel<<<dim3(nt * (nt + 1) / 2, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
+                syrk_kernel<<<dim3(nt * (nt + 1), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
                 LAUNCH_CHECK();
             }
         }

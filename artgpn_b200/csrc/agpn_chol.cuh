@@ -18,15 +18,17 @@
 //   syrk_kernel         A_ij -= L_ik L_jk^T for all trailing tiles i >= j > k, DMMA.8x8x4,
 //                       operands staged through a 4-stage cp.async shared-memory pipeline with an
 //                       XOR swizzle that makes the 64-bit fragment loads bank-conflict free.
+//                       CTA tile 128 x 64, two CTAs per SM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define TB 128                 // tile edge
+#define TB 128                 // tile edge (block column width of the factorisation)
+#define BN 64                  // n extent of one GEMM CTA tile (128 x 64, two CTAs per SM)
 #define GEMM_KC 16             // k extent of one pipeline stage
 #define GEMM_STAGES 4
-#define GEMM_STAGE_DOUBLES (2 * TB * GEMM_KC)
-#define GEMM_SMEM_BYTES (GEMM_STAGES * GEMM_STAGE_DOUBLES * 8)   // 131072
+#define GEMM_STAGE_DOUBLES ((TB + BN) * GEMM_KC)
+#define GEMM_SMEM_BYTES (GEMM_STAGES * GEMM_STAGE_DOUBLES * 8)   // 98304
 
 struct CholArgs {
     double* A;              // [nmat][n_pad][ld]
@@ -55,62 +57,69 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// swizzled offset (in doubles) of element (row, k) inside a [128][16] stage operand
+// swizzled offset (in doubles) of element (row, k) inside a [rows][16] stage operand: the 16-byte
+// chunk index is XORed with 2*(row & 3), which spreads the 8 rows x 4 k of one DMMA fragment load
+// over all 32 banks (64-bit accesses, two half-warp phases).
 __device__ __forceinline__ int swz(int row, int k) {
     return row * GEMM_KC + ((((k >> 1) ^ ((row & 3) << 1)) << 1) | (k & 1));
 }
 
 // ---------------------------------------------------------------------------------------------
-// acc[mi][ni][2] += A[128 x K] * B[128 x K]^T  (both row-major, k contiguous), 256 threads,
-// warp grid 2 (m) x 4 (n), warp tile 64 x 32 = 8 x 4 DMMA tiles.
+// acc[mi][ni][2] += A[128 x K] * B[64 x K]^T  (both row-major, k contiguous), 256 threads,
+// warp grid 4 (m) x 2 (n), warp tile 32 x 32 = 4 x 4 DMMA tiles.  Two such CTAs share an SM so
+// that one CTA's prologue / epilogue memory traffic overlaps the other's tensor work.
 // Accumulator element (mi, ni, e) of lane l lives at
-//     row = wm*64 + mi*8 + (l >> 2),  col = wn*32 + ni*8 + 2*(l & 3) + e.
+//     row = wm*32 + mi*8 + (l >> 2),  col = wn*32 + ni*8 + 2*(l & 3) + e.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gemm_load_stage(double* stage, const double* __restrict__ Ag, int lda,
                                                 const double* __restrict__ Bg, int ldb, int kc, int tid) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        int idx = tid + 256 * u;
-        int which = idx >> 10;
-        int rem = idx & 1023;
-        int row = rem >> 3;
-        int ch = rem & 7;
-        const double* src = which ? (Bg + (size_t)row * ldb + kc * GEMM_KC + ch * 2)
-                                  : (Ag + (size_t)row * lda + kc * GEMM_KC + ch * 2);
-        double* dst = stage + which * (TB * GEMM_KC) + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1);
-        cp_async16(dst, src);
+    for (int u = 0; u < 6; ++u) {
+        const int idx = tid + 256 * u;
+        if (u < 4) {
+            const int row = idx >> 3, ch = idx & 7;
+            cp_async16(stage + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1),
+                       Ag + (size_t)row * lda + kc * GEMM_KC + ch * 2);
+        } else {
+            const int rem = idx - 1024;
+            const int row = rem >> 3, ch = rem & 7;
+            cp_async16(stage + TB * GEMM_KC + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1),
+                       Bg + (size_t)row * ldb + kc * GEMM_KC + ch * 2);
+        }
     }
 }
 
-__device__ __forceinline__ void gemm_compute_stage(const double* stage, double (&acc)[8][4][2], int wm, int wn, int lane) {
+__device__ __forceinline__ void gemm_compute_stage(const double* stage, double (&acc)[4][4][2], int wm, int wn, int lane) {
     const double* As = stage;
     const double* Bs = stage + TB * GEMM_KC;
     const int r = lane >> 2;
     const int kq = lane & 3;
 #pragma unroll
     for (int ks = 0; ks < GEMM_KC / 4; ++ks) {
-        double a[8], b[4];
+        double a[4], b[4];
         const int k = ks * 4 + kq;
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) a[mi] = As[swz(wm * 64 + mi * 8 + r, k)];
+        for (int mi = 0; mi < 4; ++mi) a[mi] = As[swz(wm * 32 + mi * 8 + r, k)];
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[swz(wn * 32 + ni * 8 + r, k)];
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
 }
 
-// K must be a multiple of GEMM_KC.  All 256 threads must call.  On return every cp.async issued
-// here has completed and been consumed (safe to overwrite global A / reuse smem after a barrier).
+// K must be a multiple of GEMM_KC.  All 256 threads must call.  `active` = this warp issues the
+// tensor work (warps whose output is not needed still take part in the loads and barriers).
+// On return every cp.async issued here has completed and been consumed (safe to overwrite global
+// A / reuse smem after the trailing barrier).
 __device__ __forceinline__ void gemm_nt_tile(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
-                                             int K, double (&acc)[8][4][2], double* smem) {
+                                             int K, double (&acc)[4][4][2], double* smem, bool active = true) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int wm = warp >> 2;
-    const int wn = warp & 3;
+    const int wm = warp >> 1;
+    const int wn = warp & 1;
     const int nch = K / GEMM_KC;
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; ++s) {
@@ -123,19 +132,20 @@ __device__ __forceinline__ void gemm_nt_tile(const double* __restrict__ Ag, int 
         const int nxt = kc + GEMM_STAGES - 1;
         if (nxt < nch) gemm_load_stage(smem + (nxt % GEMM_STAGES) * GEMM_STAGE_DOUBLES, Ag, lda, Bg, ldb, nxt, tid);
         cp_async_commit();
-        gemm_compute_stage(smem + (kc % GEMM_STAGES) * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+        if (active) gemm_compute_stage(smem + (kc % GEMM_STAGES) * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
     }
     cp_async_wait<0>();
     __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
-// trailing update: A_ij -= L_ik L_jk^T, i >= j > k
-// grid.x = nt*(nt+1)/2 with nt = nblk-k-1, grid.y = nmat
+// trailing update: A_ij -= L_ik L_jk^T, i >= j > k, one CTA per 128 x 64 half tile
+// grid.x = 2 * nt*(nt+1)/2 with nt = nblk-k-1, grid.y = nmat
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) syrk_kernel(CholArgs g, int k) {
+__global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int k) {
     extern __shared__ __align__(16) double smem[];
-    const int t = blockIdx.x;
+    const int t = blockIdx.x >> 1;
+    const int h = blockIdx.x & 1;
     int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
     while (bi * (bi + 1) / 2 > t) --bi;
@@ -144,269 +154,371 @@ __global__ void __launch_bounds__(256, 1) syrk_kernel(CholArgs g, int k) {
     double* A = g.A + (size_t)blockIdx.y * g.mat_stride;
     const int ld = g.ld;
     const double* Ai = A + (size_t)ti * TB * ld + (size_t)k * TB;
-    const double* Aj = A + (size_t)tj * TB * ld + (size_t)k * TB;
-    double* C = A + (size_t)ti * TB * ld + (size_t)tj * TB;
+    const double* Aj = A + ((size_t)tj * TB + h * BN) * ld + (size_t)k * TB;
+    double* C = A + (size_t)ti * TB * ld + (size_t)tj * TB + h * BN;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
-    double acc[8][4][2];
+    const int wm = warp >> 1, wn = warp & 1;
+    // right half of a diagonal tile: rows 0..63 lie strictly above the diagonal, never read
+    const bool active = !(bi == bj && h == 1 && wm < 2);
+    double acc[4][4][2];
     // acc = -C, so that -(acc + A B^T) = C - A B^T
+    if (active) {
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int row = wm * 64 + mi * 8 + (lane >> 2);
-            const int col = wn * 32 + ni * 8 + 2 * (lane & 3);
-            const double2 c = *reinterpret_cast<const double2*>(C + (size_t)row * ld + col);
-            acc[mi][ni][0] = -c.x;
-            acc[mi][ni][1] = -c.y;
-        }
-    gemm_nt_tile(Ai, ld, Aj, ld, TB, acc, smem);
+            for (int ni = 0; ni < 4; ++ni) {
+                const int row = wm * 32 + mi * 8 + (lane >> 2);
+                const int col = wn * 32 + ni * 8 + 2 * (lane & 3);
+                const double2 c = *reinterpret_cast<const double2*>(C + (size_t)row * ld + col);
+                acc[mi][ni][0] = -c.x;
+                acc[mi][ni][1] = -c.y;
+            }
+    }
+    gemm_nt_tile(Ai, ld, Aj, ld, TB, acc, smem, active);
+    if (active) {
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int row = wm * 64 + mi * 8 + (lane >> 2);
-            const int col = wn * 32 + ni * 8 + 2 * (lane & 3);
-            double2 c;
-            c.x = -acc[mi][ni][0];
-            c.y = -acc[mi][ni][1];
-            *reinterpret_cast<double2*>(C + (size_t)row * ld + col) = c;
-        }
+            for (int ni = 0; ni < 4; ++ni) {
+                const int row = wm * 32 + mi * 8 + (lane >> 2);
+                const int col = wn * 32 + ni * 8 + 2 * (lane & 3);
+                double2 c;
+                c.x = -acc[mi][ni][0];
+                c.y = -acc[mi][ni][1];
+                *reinterpret_cast<double2*>(C + (size_t)row * ld + col) = c;
+            }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // panel solve: A_ik <- A_ik * Linv_kk^T (i > k), and rhs_i -= L_ik z_k
-// grid.x = nblk-k-1, grid.y = nmat
+// grid.x = nblk-k-1, grid.y = nmat.  Two passes per CTA over the two 64-column halves; the right
+// half goes first (it reads all 128 input columns), the left half needs only K = 64 because the
+// inverse is lower triangular -- this also makes the in-place overwrite race free.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) trsm_kernel(CholArgs g, int k) {
+__global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ double zs[TB];
+    __shared__ double red[2][TB];
     const int ti = k + 1 + blockIdx.x;
     const int mat = blockIdx.y;
     double* A = g.A + (size_t)mat * g.mat_stride;
     const int ld = g.ld;
     double* Aik = A + (size_t)ti * TB * ld + (size_t)k * TB;
     const double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
+    double* rhs = g.rhs ? g.rhs + (size_t)mat * ((size_t)g.nblk * TB) : nullptr;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
-    double acc[8][4][2];
+    const int wm = warp >> 1, wn = warp & 1;
+    if (rhs != nullptr && tid < TB) zs[tid] = rhs[(size_t)k * TB + tid];
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[4][4][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int pass = 0; pass < 2; ++pass) {
+        const int h = 1 - pass;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    gemm_nt_tile(Aik, ld, Linv, TB, TB, acc, smem);
-    // gemm_nt_tile ended with a barrier after all loads completed: in-place store is safe
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        gemm_nt_tile(Aik, ld, Linv + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem);
+        // the gemm ended with a barrier after all of its loads completed: in-place store is safe
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int row = wm * 64 + mi * 8 + (lane >> 2);
-            const int col = wn * 32 + ni * 8 + 2 * (lane & 3);
-            double2 c;
-            c.x = acc[mi][ni][0];
-            c.y = acc[mi][ni][1];
-            *reinterpret_cast<double2*>(Aik + (size_t)row * ld + col) = c;
-        }
-    if (g.rhs != nullptr) {
-        double* zs = smem;              // [128]   z_k
-        double* red = smem + TB;        // [4][128]
-        double* rhs = g.rhs + (size_t)mat * ((size_t)g.nblk * TB);
-        if (tid < TB) zs[tid] = rhs[(size_t)k * TB + tid];
-        __syncthreads();
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi) {
-            double s = 0.0;
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
-                const int col = wn * 32 + ni * 8 + 2 * (lane & 3);
-                s = fma(acc[mi][ni][0], zs[col], s);
-                s = fma(acc[mi][ni][1], zs[col + 1], s);
+                const int row = wm * 32 + mi * 8 + (lane >> 2);
+                const int col = h * BN + wn * 32 + ni * 8 + 2 * (lane & 3);
+                *reinterpret_cast<double2*>(Aik + (size_t)row * ld + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                if (rhs != nullptr) {
+                    part[mi] = fma(acc[mi][ni][0], zs[col], part[mi]);
+                    part[mi] = fma(acc[mi][ni][1], zs[col + 1], part[mi]);
+                }
             }
+    }
+    if (rhs != nullptr) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            double s = part[mi];
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if ((lane & 3) == 0) red[wn * TB + wm * 64 + mi * 8 + (lane >> 2)] = s;
+            if ((lane & 3) == 0) red[wn][wm * 32 + mi * 8 + (lane >> 2)] = s;
         }
         __syncthreads();
-        if (tid < TB) {
-            const double s = ((red[tid] + red[TB + tid]) + red[2 * TB + tid]) + red[3 * TB + tid];
-            rhs[(size_t)ti * TB + tid] -= s;
-        }
+        if (tid < TB) rhs[(size_t)ti * TB + tid] -= red[0][tid] + red[1][tid];
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// diagonal block: factor, invert, forward-solve block, log-det
-// grid.x = nmat, 256 threads as a 16 x 16 grid; thread (ti, tc) owns entries
-// (ti + 16 a, tc + 16 b), a, b in 0..7, of the 128 x 128 block in registers.
+// diagonal block: factor, invert, forward-solve block, log-det.   grid.x = nmat, 256 threads.
+//
+// The 128 x 128 block lives in shared memory (row stride 132 doubles: conflict-free DMMA
+// fragment loads).  It is processed as 8 panels of 16 columns:
+//   A  warp 0 factors the 16 x 16 diagonal block in registers (lane r owns row r; pivots and
+//      column values travel by warp shuffles) -- the only inherently serial part;
+//   B  one thread per row below solves its 16 panel entries against that block;
+//   C  the trailing 16 x 16 blocks take the rank-16 update on DMMA.8x8x4, one block per warp.
+// The inverse (needed by trsm_kernel, which applies L_kk^-T as a GEMM) is built from the 16 x 16
+// diagonal inverses by block forward substitution, again on DMMA, and kept transposed in the
+// (otherwise unused) upper triangle of the same shared tile.
 // ---------------------------------------------------------------------------------------------
-#define LS_LD 129
-#define POTRF_SMEM_BYTES ((TB * LS_LD + 2 * TB + 3 * TB) * 8)
+#define PD_LD 132
+#define PD_DV_LD 20
+#define POTRF_SMEM_DOUBLES (TB * PD_LD + 3 * TB + 8 * 16 * PD_DV_LD + 8 * 16 * PD_DV_LD)
+#define POTRF_SMEM_BYTES (POTRF_SMEM_DOUBLES * 8)
 
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
     extern __shared__ __align__(16) double smem[];
-    double* Ls = smem;                       // [128][129] scaled factor
-    double* colbuf = Ls + TB * LS_LD;        // [2][128]
-    double* piv = colbuf + 2 * TB;           // [128] pivots d_j
-    double* rs = piv + TB;                   // [128] 1/sqrt(d_j)
-    double* zs = rs + TB;                    // [128] rhs block / z
+    double* S = smem;                          // [128][132]: lower = A -> L ; strict upper = Linv^T
+    double* invd = S + TB * PD_LD;             // [128] 1 / L_jj
+    double* zs = invd + TB;                    // [128] rhs block
+    double* zout = zs + TB;                    // [128] z block
+    double* Dv = zout + TB;                    // [8][16][20] diagonal 16 x 16 inverses (full squares)
+    double* scr = Dv + 8 * 16 * PD_DV_LD;      // [8][16][20] per-warp scratch
     __shared__ int s_fail;
 
     const int mat = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int ti = tid >> 4, tc = tid & 15;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = g.ld;
     double* Akk = g.A + (size_t)mat * g.mat_stride + (size_t)k * TB * ld + (size_t)k * TB;
+    double* rhs = g.rhs ? g.rhs + (size_t)mat * ((size_t)g.nblk * TB) + (size_t)k * TB : nullptr;
     if (tid == 0) s_fail = 0;
 
-    double a[8][8];
-#pragma unroll
-    for (int aa = 0; aa < 8; ++aa)
-#pragma unroll
-        for (int bb = 0; bb < 8; ++bb) {
-            const int i = ti + 16 * aa, c = tc + 16 * bb;
-            a[aa][bb] = (i >= c) ? Akk[(size_t)i * ld + c] : 0.0;
-        }
+    // ---- load the lower triangle (coalesced rows; 2 rows per pass) --------------------------------
+    for (int i = tid >> 7; i < TB; i += 2) {
+        const int c = tid & 127;
+        S[i * PD_LD + c] = (c <= i) ? Akk[(size_t)i * ld + c] : 0.0;
+    }
+    if (rhs != nullptr && tid < TB) zs[tid] = rhs[tid];
+    __syncthreads();
 
-    // ---- factor: right-looking, column j broadcast unscaled, update uses 1/d_j -----------------
-    for (int j = 0; j < TB; ++j) {
-        double* cb = colbuf + (j & 1) * TB;
-        const int bj = j >> 4;
-        if (tc == (j & 15)) {
+    // ---- factor ---------------------------------------------------------------------------------
+    for (int pb = 0; pb < 8; ++pb) {
+        const int c0 = pb * 16;
+        if (warp == 0) {
+            // A: 16 x 16 diagonal block, lane r (and its mirror r + 16) owns row r
+            const int r = lane & 15;
+            double d[16];
 #pragma unroll
-            for (int bb = 0; bb < 8; ++bb)
-                if (bb == bj) {
+            for (int c = 0; c < 16; ++c) d[c] = S[(c0 + r) * PD_LD + c0 + c];
+            double myrs = 1.0;
+            int bad = 0;
 #pragma unroll
-                    for (int aa = 0; aa < 8; ++aa) cb[ti + 16 * aa] = a[aa][bb];
+            for (int j = 0; j < 16; ++j) {
+                double piv = __shfl_sync(0xffffffffu, d[j], j, 16);
+                if (!(piv > 0.0) || isinf(piv)) {      // LAPACK dpotrf: ajj <= 0 or NaN -> not PD
+                    bad = 1;
+                    piv = 1.0;
                 }
-        }
-        __syncthreads();
-        double d = cb[j];
-        if (!(d > 0.0) || isinf(d)) {      // LAPACK dpotrf: ajj <= 0 or NaN -> info = j+1
-            if (tid == 0) s_fail = 1;
-            d = 1.0;
-        }
-        if (tid == 0) piv[j] = d;
-        const double invd = 1.0 / d;
+                const double rs = rsqrt(piv);            // <= 1 ulp; keeps the serial chain short
+                if (j == r) myrs = rs;
+                const double l = (j == r) ? sqrt(piv) : d[j] * rs;
+                d[j] = l;
 #pragma unroll
-        for (int bb = 0; bb < 8; ++bb) {
-            const int c = tc + 16 * bb;
-            if (c > j) {
-                const double lc = cb[c] * invd;
-#pragma unroll
-                for (int aa = 0; aa < 8; ++aa) {
-                    const int i = ti + 16 * aa;
-                    if (i >= c) a[aa][bb] = fma(-cb[i], lc, a[aa][bb]);
+                for (int c = j + 1; c < 16; ++c) {
+                    const double lc = __shfl_sync(0xffffffffu, l, c, 16);
+                    d[c] = fma(-l, lc, d[c]);
                 }
             }
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c <= r) S[(c0 + r) * PD_LD + c0 + c] = d[c];
+                invd[c0 + r] = myrs;
+            }
+            if (bad && lane == 0) s_fail = 1;
+        }
+        __syncthreads();
+        // B: rows below the diagonal block, one thread per row: x L_D^T = b
+        const int nrows = TB - c0 - 16;
+        if (tid < nrows) {
+            double* rowp = S + (c0 + 16 + tid) * PD_LD + c0;
+            double x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                double sacc = rowp[j];
+#pragma unroll
+                for (int m = 0; m < j; ++m) sacc = fma(-x[m], S[(c0 + j) * PD_LD + c0 + m], sacc);
+                x[j] = sacc * invd[c0 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rowp[j] = x[j];
+        }
+        __syncthreads();
+        // C: trailing blocks (bi >= bj > pb) -= X_bi X_bj^T, one 16 x 16 block per warp and pass
+        const int nb = 7 - pb;
+        const int nblocks = nb * (nb + 1) / 2;
+        for (int t = warp; t < nblocks; t += 8) {
+            int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+            while (bi * (bi + 1) / 2 > t) --bi;
+            const int bj = t - bi * (bi + 1) / 2;
+            const int r0 = (pb + 1 + bi) * 16, q0 = (pb + 1 + bj) * 16;
+            double acc[2][2][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    const double2 c = *reinterpret_cast<const double2*>(
+                        S + (r0 + 8 * mi + (lane >> 2)) * PD_LD + q0 + 8 * ni + 2 * (lane & 3));
+                    acc[mi][ni][0] = c.x;
+                    acc[mi][ni][1] = c.y;
+                }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                double a[2], b[2];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) a[mi] = -S[(r0 + 8 * mi + (lane >> 2)) * PD_LD + c0 + 4 * k4 + (lane & 3)];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) b[ni] = S[(q0 + 8 * ni + (lane >> 2)) * PD_LD + c0 + 4 * k4 + (lane & 3)];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni)
+                    *reinterpret_cast<double2*>(S + (r0 + 8 * mi + (lane >> 2)) * PD_LD + q0 + 8 * ni + 2 * (lane & 3)) =
+                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+        __syncthreads();
+    }
+
+    // ---- write L back (lower triangle incl. diagonal) -----------------------------------------------
+    for (int i = tid >> 7; i < TB; i += 2) {
+        const int c = tid & 127;
+        if (c <= i) Akk[(size_t)i * ld + c] = S[i * PD_LD + c];
+    }
+
+    // ---- inverse, step 1: the eight 16 x 16 diagonal inverses, warp w -> block w, lane c -> column c --
+    {
+        const int c0 = warp * 16;
+        const int c = lane & 15;
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int m = 0; m < i; ++m) sacc = fma(-S[(c0 + i) * PD_LD + c0 + m], x[m], sacc);
+            x[i] = (i >= c) ? sacc * invd[c0 + i] : 0.0;
+        }
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Dv[warp * 16 * PD_DV_LD + i * PD_DV_LD + c] = x[i];
         }
     }
     __syncthreads();
-    if (tid < TB) rs[tid] = 1.0 / sqrt(piv[tid]);
-    if (g.rhs != nullptr && tid < TB) zs[tid] = g.rhs[(size_t)mat * ((size_t)g.nblk * TB) + (size_t)k * TB + tid];
-    __syncthreads();
-    // scale columns, publish L to shared memory and write it back
+    // ---- inverse, step 2: block rows i = 1..7:  X_ij = -Dinv_i * sum_{m=j}^{i-1} L_im X_mj  (warp j) --
+    for (int i = 1; i < 8; ++i) {
+        if (warp < i) {
+            const int j = warp;
+            double acc[2][2][2];
 #pragma unroll
-    for (int aa = 0; aa < 8; ++aa)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int bb = 0; bb < 8; ++bb) {
-            const int i = ti + 16 * aa, c = tc + 16 * bb;
-            double v = 0.0;
-            if (i > c) v = a[aa][bb] * rs[c];
-            else if (i == c) v = sqrt(piv[c]);
-            Ls[i * LS_LD + c] = v;
-            if (i >= c) Akk[(size_t)i * ld + c] = v;
-        }
-
-    // ---- inverse: X = L^-1 by the same sweep (row j of X final at step j) ----------------------
-    double (&x)[8][8] = a;
+                for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int m = j; m < i; ++m) {
 #pragma unroll
-    for (int aa = 0; aa < 8; ++aa)
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    double a[2], b[2];
+                    const int kk = 4 * k4 + (lane & 3);
 #pragma unroll
-        for (int bb = 0; bb < 8; ++bb) x[aa][bb] = (ti + 16 * aa == tc + 16 * bb) ? 1.0 : 0.0;
-    for (int j = 0; j < TB; ++j) {
-        double* rb = colbuf + (j & 1) * TB;
-        const int aj = j >> 4;
-        if (ti == (j & 15)) {
+                    for (int mi = 0; mi < 2; ++mi) a[mi] = S[(16 * i + 8 * mi + (lane >> 2)) * PD_LD + 16 * m + kk];
 #pragma unroll
-            for (int aa = 0; aa < 8; ++aa)
-                if (aa == aj) {
-#pragma unroll
-                    for (int bb = 0; bb < 8; ++bb) {
-                        const double v = x[aa][bb] * rs[j];
-                        x[aa][bb] = v;
-                        rb[tc + 16 * bb] = v;
+                    for (int ni = 0; ni < 2; ++ni) {
+                        const int n = 8 * ni + (lane >> 2);
+                        b[ni] = (m == j) ? Dv[j * 16 * PD_DV_LD + kk * PD_DV_LD + n]      // X_jj = Dinv_j [k][n]
+                                         : S[(16 * j + n) * PD_LD + 16 * m + kk];       // X_mj[k][n], stored transposed
                     }
-                }
-        }
-        __syncthreads();   // also orders the Ls writes above before the first read below
 #pragma unroll
-        for (int aa = 0; aa < 8; ++aa) {
-            const int i = ti + 16 * aa;
-            if (i > j) {
-                const double lij = Ls[i * LS_LD + j];
+                    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int bb = 0; bb < 8; ++bb) {
-                    const int c = tc + 16 * bb;
-                    if (c <= j) x[aa][bb] = fma(-lij, rb[c], x[aa][bb]);
+                        for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
                 }
             }
-        }
-    }
-    // write the inverse (full tile, zeros above the diagonal)
-    double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
+            // P -> per-warp scratch (as a B operand: [k][n]), then Y = -Dinv_i P
+            double* sc = scr + warp * 16 * PD_DV_LD;
 #pragma unroll
-    for (int aa = 0; aa < 8; ++aa)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int bb = 0; bb < 8; ++bb) {
-            const int i = ti + 16 * aa, c = tc + 16 * bb;
-            Linv[i * TB + c] = (i >= c) ? x[aa][bb] : 0.0;
-        }
-
-    // ---- z_k = X r_k ; |z_k|^2 ; sum log L_jj -------------------------------------------------
-    __syncthreads();
-    if (g.rhs != nullptr) {
-        double* zout = colbuf;  // [128] reuse
+                for (int ni = 0; ni < 2; ++ni) {
+                    const int rr = 8 * mi + (lane >> 2), cc = 8 * ni + 2 * (lane & 3);
+                    sc[rr * PD_DV_LD + cc] = acc[mi][ni][0];
+                    sc[rr * PD_DV_LD + cc + 1] = acc[mi][ni][1];
+                    acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                }
+            __syncwarp();
 #pragma unroll
-        for (int aa = 0; aa < 8; ++aa) {
-            double s = 0.0;
+            for (int k4 = 0; k4 < 4; ++k4) {
+                double a[2], b[2];
+                const int kk = 4 * k4 + (lane & 3);
 #pragma unroll
-            for (int bb = 0; bb < 8; ++bb) s = fma(x[aa][bb], zs[tc + 16 * bb], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 8);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (tc == 0) zout[ti + 16 * aa] = s;
+                for (int mi = 0; mi < 2; ++mi) a[mi] = -Dv[i * 16 * PD_DV_LD + (8 * mi + (lane >> 2)) * PD_DV_LD + kk];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) b[ni] = sc[kk * PD_DV_LD + 8 * ni + (lane >> 2)];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            // X_ij[r][c] -> transposed into the upper triangle: S[16 j + c][16 i + r]
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    const int rr = 8 * mi + (lane >> 2), cc = 8 * ni + 2 * (lane & 3);
+                    S[(16 * j + cc) * PD_LD + 16 * i + rr] = acc[mi][ni][0];
+                    S[(16 * j + cc + 1) * PD_LD + 16 * i + rr] = acc[mi][ni][1];
+                }
+            __syncwarp();
         }
         __syncthreads();
-        if (tid < TB) g.rhs[(size_t)mat * ((size_t)g.nblk * TB) + (size_t)k * TB + tid] = zout[tid];
-        if (tid < 32) {
-            double q = 0.0, l = 0.0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double z = zout[tid + 32 * u];
-                q = fma(z, z, q);
-                l += log(sqrt(piv[tid + 32 * u]));
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                q += __shfl_xor_sync(0xffffffffu, q, o);
-                l += __shfl_xor_sync(0xffffffffu, l, o);
-            }
-            if (tid == 0) {
-                g.quad[mat] += q;
-                g.logdet[mat] += l;
-                if (s_fail && g.info[mat] == 0) g.info[mat] = 1;
-            }
+    }
+
+    // ---- write the inverse (full tile, zeros above the diagonal) -------------------------------------
+    double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
+    for (int R = tid >> 7; R < TB; R += 2) {
+        const int C = tid & 127;
+        double v = 0.0;
+        if ((C >> 4) == (R >> 4)) v = Dv[(R >> 4) * 16 * PD_DV_LD + (R & 15) * PD_DV_LD + (C & 15)];
+        else if (C < R) v = S[C * PD_LD + R];
+        Linv[R * TB + C] = v;
+    }
+
+    // ---- z_k = Linv r_k ; |z_k|^2 ; sum log L_jj ------------------------------------------------------
+    if (rhs != nullptr) {
+        if (tid < TB) {
+            const int R = tid;
+            const int b0 = (R >> 4) * 16;
+            double sacc = 0.0;
+            for (int C = 0; C < b0; ++C) sacc = fma(S[C * PD_LD + R], zs[C], sacc);
+            for (int C = b0; C <= R; ++C) sacc = fma(Dv[(R >> 4) * 16 * PD_DV_LD + (R & 15) * PD_DV_LD + (C - b0)], zs[C], sacc);
+            zout[R] = sacc;
+            rhs[R] = sacc;
         }
-    } else if (tid < 32) {
-        double l = 0.0;
+        __syncthreads();
+    }
+    if (tid < 32) {
+        double qv = 0.0, lv = 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) l += log(sqrt(piv[tid + 32 * u]));
+        for (int u = 0; u < 4; ++u) {
+            const int j = tid + 32 * u;
+            if (rhs != nullptr) {
+                const double z = zout[j];
+                qv = fma(z, z, qv);
+            }
+            lv += log(S[j * PD_LD + j]);
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            qv += __shfl_xor_sync(0xffffffffu, qv, o);
+            lv += __shfl_xor_sync(0xffffffffu, lv, o);
+        }
         if (tid == 0) {
-            g.logdet[mat] += l;
+            if (rhs != nullptr) g.quad[mat] += qv;
+            g.logdet[mat] += lv;
             if (s_fail && g.info[mat] == 0) g.info[mat] = 1;
         }
     }

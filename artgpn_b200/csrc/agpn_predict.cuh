@@ -31,15 +31,15 @@ struct PredArgs {
     double* std_out;         // [M]
 };
 
-__global__ void __launch_bounds__(256, 1) predict_kernel(const __grid_constant__ Structure S, const PredArgs g) {
+__global__ void __launch_bounds__(256, 2) predict_kernel(const __grid_constant__ Structure S, const PredArgs g) {
     extern __shared__ __align__(16) double smem[];
     __shared__ PKern s_node[AGPN_MAXQ];
     __shared__ PKern s_weight[AGPN_MAXQ];
     __shared__ double s_ts[TB], s_tn[TB], s_z[TB];
-    __shared__ double s_red[2][4][TB];
+    __shared__ double s_red[2][2][TB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp >> 1, wn = warp & 1;
     const int q = S.q;
     const int m0 = blockIdx.x * TB;
     if (tid < q) s_node[tid] = prep_kernel(0, S.node_kind[tid], g.theta + S.node_off[tid]);
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256, 1) predict_kernel(const __grid_constant__
     }
     double* Vrow = g.V + (size_t)m0 * g.n_pad;
     double mu_acc = 0.0, v_acc = 0.0;     // threads < 128: one prediction point each
-    double acc[8][4][2];
+    double acc[4][4][2];
 
     for (int k = 0; k < g.nblk; ++k) {
         __syncthreads();
@@ -63,77 +63,89 @@ __global__ void __launch_bounds__(256, 1) predict_kernel(const __grid_constant__
             s_z[tid] = g.z[gn];
         }
         __syncthreads();
-        // ---- acc = -K*[rows, k] ----------------------------------------------------------------
+        double* Vt = Vrow + (size_t)k * TB;
+        // ---- T[:, half] = K*[rows, k] - V[rows, 0:k] L[k, 0:k]^T, two 64-column halves -------------
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) {
-            const int row = wm * 64 + mi * 8 + (lane >> 2);
-            const int gm = m0 + row;
-            const double t1 = s_ts[row];
+            for (int mi = 0; mi < 4; ++mi) {
+                const int row = wm * 32 + mi * 8 + (lane >> 2);
+                const int gm = m0 + row;
+                const double t1 = s_ts[row];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
+                for (int ni = 0; ni < 4; ++ni) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int col = wn * 32 + ni * 8 + 2 * (lane & 3) + e;
-                    const int gn = k * TB + col;
-                    double v = 0.0;
-                    if (gm < g.M && gn < g.N) {
-                        const double t2 = s_tn[col];
-                        const double r = t1 - t2;
-                        const bool dg = g.square && gm == gn;
-                        for (int j = 0; j < q; ++j) {
-                            const PKern& kn = s_node[j];
-                            const PKern& kw = s_weight[j];
-                            const double f = kn.kind == K_CONSTANT ? kn.amp : kn.amp * kern_shape(kn, r, t1, t2, dg);
-                            const double wv = kw.kind == K_CONSTANT ? kw.amp : kw.amp * kern_shape(kw, r, t1, t2, dg);
-                            v = fma(wv, f, v);
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = h * BN + wn * 32 + ni * 8 + 2 * (lane & 3) + e;
+                        const int gn = k * TB + col;
+                        double v = 0.0;
+                        if (gm < g.M && gn < g.N) {
+                            const double t2 = s_tn[col];
+                            const double r = t1 - t2;
+                            const bool dg = g.square && gm == gn;
+                            for (int j = 0; j < q; ++j) {
+                                const PKern& kn = s_node[j];
+                                const PKern& kw = s_weight[j];
+                                const double f = kn.kind == K_CONSTANT ? kn.amp : kn.amp * kern_shape(kn, r, t1, t2, dg);
+                                const double wv = kw.kind == K_CONSTANT ? kw.amp : kw.amp * kern_shape(kw, r, t1, t2, dg);
+                                v = fma(wv, f, v);
+                            }
                         }
+                        acc[mi][ni][e] = -v;
                     }
-                    acc[mi][ni][e] = -v;
+                }
+            }
+            if (k > 0) gemm_nt_tile(Vrow, g.n_pad, g.L + ((size_t)k * TB + h * BN) * g.ld, g.ld, k * TB, acc, smem);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int row = wm * 32 + mi * 8 + (lane >> 2);
+                    const int col = h * BN + wn * 32 + ni * 8 + 2 * (lane & 3);
+                    *reinterpret_cast<double2*>(Vt + (size_t)row * g.n_pad + col) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+                }
+        }
+        __syncthreads();
+        // ---- V[rows, k] = T Linv_kk^T : right half first (reads all of T), left half K = 64 -------
+        double pm[4] = {0.0, 0.0, 0.0, 0.0}, pv[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int pass = 0; pass < 2; ++pass) {
+            const int h = 1 - pass;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            gemm_nt_tile(Vt, g.n_pad, g.Linv + (size_t)k * TB * TB + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int row = wm * 32 + mi * 8 + (lane >> 2);
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int col = h * BN + wn * 32 + ni * 8 + 2 * (lane & 3);
+                    const double x0 = acc[mi][ni][0], x1 = acc[mi][ni][1];
+                    *reinterpret_cast<double2*>(Vt + (size_t)row * g.n_pad + col) = make_double2(x0, x1);
+                    pm[mi] = fma(x0, s_z[col], pm[mi]);
+                    pm[mi] = fma(x1, s_z[col + 1], pm[mi]);
+                    pv[mi] = fma(x0, x0, pv[mi]);
+                    pv[mi] = fma(x1, x1, pv[mi]);
                 }
             }
         }
-        // ---- acc += V[rows, 0:k] L[k, 0:k]^T  ->  T = -acc ---------------------------------------
-        if (k > 0) gemm_nt_tile(Vrow, g.n_pad, g.L + (size_t)k * TB * g.ld, g.ld, k * TB, acc, smem);
-        double* Vt = Vrow + (size_t)k * TB;
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int row = wm * 64 + mi * 8 + (lane >> 2);
-                const int col = wn * 32 + ni * 8 + 2 * (lane & 3);
-                *reinterpret_cast<double2*>(Vt + (size_t)row * g.n_pad + col) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
-                acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            }
-        __syncthreads();
-        // ---- V[rows, k] = T Linv_kk^T ----------------------------------------------------------
-        gemm_nt_tile(Vt, g.n_pad, g.Linv + (size_t)k * TB * TB, TB, TB, acc, smem);
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi) {
-            double sm = 0.0, sv = 0.0;
-            const int row = wm * 64 + mi * 8 + (lane >> 2);
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int col = wn * 32 + ni * 8 + 2 * (lane & 3);
-                const double x0 = acc[mi][ni][0], x1 = acc[mi][ni][1];
-                *reinterpret_cast<double2*>(Vt + (size_t)row * g.n_pad + col) = make_double2(x0, x1);
-                sm = fma(x0, s_z[col], sm);
-                sm = fma(x1, s_z[col + 1], sm);
-                sv = fma(x0, x0, sv);
-                sv = fma(x1, x1, sv);
-            }
+        for (int mi = 0; mi < 4; ++mi) {
+            double sm = pm[mi], sv = pv[mi];
             sm += __shfl_xor_sync(0xffffffffu, sm, 1);
             sm += __shfl_xor_sync(0xffffffffu, sm, 2);
             sv += __shfl_xor_sync(0xffffffffu, sv, 1);
             sv += __shfl_xor_sync(0xffffffffu, sv, 2);
             if ((lane & 3) == 0) {
+                const int row = wm * 32 + mi * 8 + (lane >> 2);
                 s_red[0][wn][row] = sm;
                 s_red[1][wn][row] = sv;
             }
         }
         __syncthreads();
         if (tid < TB) {
-            mu_acc += ((s_red[0][0][tid] + s_red[0][1][tid]) + s_red[0][2][tid]) + s_red[0][3][tid];
-            v_acc += ((s_red[1][0][tid] + s_red[1][1][tid]) + s_red[1][2][tid]) + s_red[1][3][tid];
+            mu_acc += s_red[0][0][tid] + s_red[0][1][tid];
+            v_acc += s_red[1][0][tid] + s_red[1][1][tid];
         }
     }
     if (tid < TB) {

@@ -58,12 +58,13 @@ def _cpu_worker(args):
     return out
 
 
-def cpu_evals_per_sec(cfg, wk, n_evals, ncores):
+def cpu_evals_per_sec(cfg, wk, n_evals, ncores, W_total=None):
     """Reference-style parallel mode (examples/Sun/01_emcee.py:3-4,119-122): a process pool with
     OMP_NUM_THREADS=1, one walker per task.  Returns (evals/s, values, seconds)."""
     import multiprocessing as mp
     from artgpn_b200 import synth
-    theta = synth.make_walkers(max(n_evals, 1), p=cfg["p"], q=cfg["q"], weights=wk, seed=1)[:n_evals]
+    # the FIRST n_evals rows of the very batch the GPU arm evaluates (make_walkers draws column-wise)
+    theta = synth.make_walkers(max(W_total or cfg["W"], n_evals), p=cfg["p"], q=cfg["q"], weights=wk, seed=1)[:n_evals]
     old = os.environ.get("OMP_NUM_THREADS")
     os.environ["OMP_NUM_THREADS"] = "1"          # inherited by the spawned workers before they import numpy
     try:
