@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -80,6 +81,13 @@ struct agpn_ctx {
     struct Ev { cudaEvent_t a, b; int ph; };
     std::vector<Ev> evs;
     bool attrs_set = false;
+    int group = 4;             // block columns per wide trailing update (AGPN_GROUP)
+    // sub-batch streams: the matrices of a batch are split over nsub streams so that one sub-batch's
+    // small serial kernels (diagonal block, panel solve) overlap another's wide tensor update
+    int nsub = 3;              // AGPN_STREAMS
+    cudaStream_t sub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static double host_mean(const double* t, int n) {
@@ -122,6 +130,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     c->npad = c->nblk * TB;
     c->tmean = host_mean(time, N);
     c->t0 = time[0];
+    if (const char* e = getenv("AGPN_GROUP")) c->group = atoi(e) > 0 ? atoi(e) : 4;
     memset(&c->S, 0, sizeof(Structure));
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_t, sizeof(double) * N)) != cudaSuccess ||
@@ -138,6 +147,18 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
         agpn_destroy(c);
         return 1;
     }
+    if (const char* e = getenv("AGPN_STREAMS")) c->nsub = atoi(e);
+    if (c->nsub < 1) c->nsub = 1;
+    if (c->nsub > 8) c->nsub = 8;
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) c->nsub = 1;
+    for (int i = 0; i < c->nsub && c->nsub > 1; ++i) {
+        if (cudaStreamCreateWithFlags(&c->sub[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+            g_err = "agpn_create: cannot create sub-batch streams";
+            agpn_destroy(c);
+            return 1;
+        }
+    }
     *out = c;
     return 0;
 }
@@ -149,6 +170,11 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    for (int i = 0; i < 8; ++i) {
+        if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     cudaFree(c->d_t); cudaFree(c->d_y); cudaFree(c->d_yerr);
     cudaFree(c->d_A); cudaFree(c->d_Linv); cudaFree(c->d_rhs); cudaFree(c->d_logdet); cudaFree(c->d_quad);
     cudaFree(c->d_info); cudaFree(c->d_theta); cudaFree(c->d_out); cudaFree(c->d_status);
@@ -288,28 +314,39 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
     return 0;
 }
 
-// factorise nmat matrices in place (+ optional rhs), all on `st`
+// factorise nmat matrices in place (+ optional rhs), all on `st`.
+// Block columns are processed in groups of c->group: inside a group, block column k first takes
+// the (narrow) update from the group's earlier columns, then its diagonal block is factorised and
+// its panel solved; after the group the whole trailing matrix takes ONE update of depth
+// 128 * group (wide).  group = 1 is the plain right-looking algorithm.
 static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor) {
     size_t local_cursor = 0;
     size_t& cur = cursor ? *cursor : local_cursor;
-    for (int k = 0; k < g.nblk; ++k) {
-        {
-            PhaseScope ps(c, st, PH_DIAG, cur);
-            potrf_diag_kernel<<<g.nmat, 256, POTRF_SMEM_BYTES, st>>>(g, k);
-            LAUNCH_CHECK();
-        }
-        const int nt = g.nblk - k - 1;
-        if (nt > 0) {
-            {
-                PhaseScope ps(c, st, PH_TRSM, cur);
-                trsm_kernel<<<dim3(nt, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
-                LAUNCH_CHECK();
-            }
-            {
+    const int group = c->group < 1 ? 1 : c->group;
+    for (int k0 = 0; k0 < g.nblk; k0 += group) {
+        const int kend = (k0 + group < g.nblk) ? k0 + group : g.nblk;
+        for (int k = k0; k < kend; ++k) {
+            if (k > k0) {
                 PhaseScope ps(c, st, PH_SYRK, cur);
-                syrk_kernel<<<dim3(nt * (nt + 1), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
+                syrk_kernel<<<dim3(2 * (g.nblk - k), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
                 LAUNCH_CHECK();
             }
+            {
+                PhaseScope ps(c, st, PH_DIAG, cur);
+                potrf_diag_kernel<<<g.nmat, 256, POTRF_SMEM_BYTES, st>>>(g, k);
+                LAUNCH_CHECK();
+            }
+            if (k < g.nblk - 1) {
+                PhaseScope ps(c, st, PH_TRSM, cur);
+                trsm_kernel<<<dim3(g.nblk - k - 1, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
+                LAUNCH_CHECK();
+            }
+        }
+        const int nt = g.nblk - kend;
+        if (nt > 0) {
+            PhaseScope ps(c, st, PH_SYRK, cur);
+            syrk_kernel<<<dim3(nt * (nt + 1), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
+            LAUNCH_CHECK();
         }
     }
     return 0;
@@ -392,7 +429,29 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
         g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = nmat;
         g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
         g.info = d_infoflag;
-        if (run_cholesky(c, g, st, &cur)) return 1;
+        const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
+        if (nsub == 1) {
+            if (run_cholesky(c, g, st, &cur)) return 1;
+        } else {
+            // fork: every sub-stream waits for the assembly, factorises its slice of the matrices
+            // (walker results do not depend on the split), and the caller's stream joins them all
+            CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+            for (int si = 0; si < nsub; ++si) {
+                const int m0 = (int)((long long)nmat * si / nsub), m1 = (int)((long long)nmat * (si + 1) / nsub);
+                CholArgs gs = g;
+                gs.A = g.A + (size_t)m0 * g.mat_stride;
+                gs.Linv = g.Linv + (size_t)m0 * TB * TB;
+                gs.rhs = g.rhs + (size_t)m0 * np;
+                gs.logdet = g.logdet + m0;
+                gs.quad = g.quad + m0;
+                gs.info = g.info + m0;
+                gs.nmat = m1 - m0;
+                CUDA_TRY(cudaStreamWaitEvent(c->sub[si], c->ev_fork, 0));
+                if (run_cholesky(c, gs, c->sub[si], nullptr)) return 1;
+                CUDA_TRY(cudaEventRecord(c->ev_join[si], c->sub[si]));
+                CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[si], 0));
+            }
+        }
         double* d_out = out_on_device ? out + w0 : c->d_out;
         {
             PhaseScope ps(c, st, PH_FINAL, cur);
@@ -622,6 +681,7 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     cudaStream_t st = (cudaStream_t)stream;
     agpn_ctx tmp;
     tmp.device = device;
+    if (const char* e = getenv("AGPN_GROUP")) tmp.group = atoi(e) > 0 ? atoi(e) : 4;
     if (set_kernel_attrs(&tmp)) return 1;
     double* d_linv = nullptr;
     CUDA_TRY(cudaMalloc(&d_linv, sizeof(double) * (size_t)nmat * TB * TB));

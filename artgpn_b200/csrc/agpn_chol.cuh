@@ -6,8 +6,10 @@
 // upper factor U of cho_factor(lower=False) is L^T, same diagonal).  Padding rows carry the
 // identity, so the factor of the padded matrix is [L 0; 0 I] and log-det / solves are unchanged.
 //
-// Right-looking tile algorithm, one step per 128-wide block column k, three kernels per step
-// over ALL matrices of the batch (grid.y = matrix):
+// Tile algorithm over 128-wide block columns, right-looking between groups of `group` block
+// columns and left-looking inside a group (see run_cholesky in agpn_api.cu): the wide trailing
+// update applies a whole group at once (K = 128 * group).  Three kernels, each over ALL matrices
+// of the batch (grid.y = matrix):
 //   potrf_diag_kernel   one CTA per matrix: 128x128 diagonal block factorised in registers
 //                       (2-D cyclic thread ownership, one column broadcast per step through
 //                       shared memory), its inverse by the same sweep, and -- folded in -- the
@@ -139,22 +141,34 @@ __device__ __forceinline__ void gemm_nt_tile(const double* __restrict__ Ag, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// trailing update: A_ij -= L_ik L_jk^T, i >= j > k, one CTA per 128 x 64 half tile
-// grid.x = 2 * nt*(nt+1)/2 with nt = nblk-k-1, grid.y = nmat
+// trailing update with `depth` already-factored block columns kfirst .. kfirst+depth-1 at once:
+//     A_ij -= [L_i,kfirst .. L_i,kfirst+depth-1] [L_j,kfirst .. ]^T      (K = 128 * depth)
+// The block columns of one block row are adjacent in memory, so a deeper update is the same
+// NT GEMM with a longer k loop: the C tile is read and written once per `depth` panels and the
+// pipeline prologue / epilogue is amortised over depth x the tensor work.
+//   narrow = 1: only block column j0 (tiles (i, j0), i >= j0)      grid.x = 2 * (nblk - j0)
+//   narrow = 0: all tiles i >= j >= j0                              grid.x = nt * (nt + 1), nt = nblk - j0
+// one CTA per 128 x 64 half tile; grid.y = nmat
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int k) {
+__global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, int depth, int j0, int narrow) {
     extern __shared__ __align__(16) double smem[];
     const int t = blockIdx.x >> 1;
     const int h = blockIdx.x & 1;
-    int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-    while (bi * (bi + 1) / 2 > t) --bi;
-    const int bj = t - bi * (bi + 1) / 2;
-    const int ti = k + 1 + bi, tj = k + 1 + bj;
+    int bi, bj;
+    if (narrow) {
+        bi = t;
+        bj = 0;
+    } else {
+        bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        while (bi * (bi + 1) / 2 > t) --bi;
+        bj = t - bi * (bi + 1) / 2;
+    }
+    const int ti = j0 + bi, tj = j0 + bj;
     double* A = g.A + (size_t)blockIdx.y * g.mat_stride;
     const int ld = g.ld;
-    const double* Ai = A + (size_t)ti * TB * ld + (size_t)k * TB;
-    const double* Aj = A + ((size_t)tj * TB + h * BN) * ld + (size_t)k * TB;
+    const double* Ai = A + (size_t)ti * TB * ld + (size_t)kfirst * TB;
+    const double* Aj = A + ((size_t)tj * TB + h * BN) * ld + (size_t)kfirst * TB;
     double* C = A + (size_t)ti * TB * ld + (size_t)tj * TB + h * BN;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -175,7 +189,7 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int k) {
                 acc[mi][ni][1] = -c.y;
             }
     }
-    gemm_nt_tile(Ai, ld, Aj, ld, TB, acc, smem, active);
+    gemm_nt_tile(Ai, ld, Aj, ld, depth * TB, acc, smem, active);
     if (active) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
