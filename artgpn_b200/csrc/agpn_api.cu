@@ -82,6 +82,7 @@ struct agpn_ctx {
     std::vector<Ev> evs;
     bool attrs_set = false;
     int group = 4;             // block columns per wide trailing update (AGPN_GROUP)
+    bool no_fast_asm = false;  // AGPN_GENERIC_ASM=1 forces the generic assembly kernel
     // sub-batch streams: the matrices of a batch are split over nsub streams so that one sub-batch's
     // small serial kernels (diagonal block, panel solve) overlap another's wide tensor update
     int nsub = 3;              // AGPN_STREAMS
@@ -131,6 +132,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     c->tmean = host_mean(time, N);
     c->t0 = time[0];
     if (const char* e = getenv("AGPN_GROUP")) c->group = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char* e = getenv("AGPN_GENERIC_ASM")) c->no_fast_asm = atoi(e) != 0;
     memset(&c->S, 0, sizeof(Structure));
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_t, sizeof(double) * N)) != cudaSuccess ||
@@ -352,6 +354,31 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
     return 0;
 }
 
+// the likelihood-path assembly has a specialised kernel when every node is SE / Periodic /
+// QuasiPeriodic and every weight Constant / SE (the reference's example networks and the bench)
+static bool fast_assembly_ok(const agpn_ctx* c, const AsmArgs& a, bool* wse) {
+    if (!a.lower_only || !a.square || !a.add_err || !a.add_jit || !a.pad_identity || !a.vec2) return false;
+    if (c->no_fast_asm || c->S.q > ASMF_MAXQ || a.nser > 4 || a.rows_out % ASM_TILE || a.cols_out != a.rows_out) return false;
+    *wse = false;
+    for (int j = 0; j < c->S.q; ++j) {
+        const int k = c->S.node_kind[j];
+        if (k != K_SE && k != K_PERIODIC && k != K_QP) return false;
+    }
+    for (int s = 0; s < a.nser; ++s)
+        for (int j = 0; j < c->S.q; ++j) {
+            const int k = c->S.weight_kind[j + c->S.q * (a.series0 + s)];
+            if (k == K_SE) *wse = true;
+            else if (k != K_CONSTANT) return false;
+        }
+    return true;
+}
+
+template <int P>
+static void launch_fast(const agpn_ctx* c, const AsmArgs& a, bool wse, dim3 grid, cudaStream_t st) {
+    if (wse) assemble_fast_kernel<P, true><<<grid, 256, 0, st>>>(c->S, a);
+    else assemble_fast_kernel<P, false><<<grid, 256, 0, st>>>(c->S, a);
+}
+
 static int launch_assemble(agpn_ctx* c, AsmArgs& a, int W, cudaStream_t st) {
     int tiles;
     if (a.lower_only) {
@@ -360,7 +387,18 @@ static int launch_assemble(agpn_ctx* c, AsmArgs& a, int W, cudaStream_t st) {
     } else {
         tiles = ((a.rows_out + ASM_TILE - 1) / ASM_TILE) * ((a.cols_out + ASM_TILE - 1) / ASM_TILE);
     }
-    assemble_kernel<<<dim3(tiles, W), 256, 0, st>>>(c->S, a);
+    bool wse = false;
+    if (fast_assembly_ok(c, a, &wse)) {
+        const dim3 grid(tiles, W);
+        switch (a.nser) {
+            case 1: launch_fast<1>(c, a, wse, grid, st); break;
+            case 2: launch_fast<2>(c, a, wse, grid, st); break;
+            case 3: launch_fast<3>(c, a, wse, grid, st); break;
+            default: launch_fast<4>(c, a, wse, grid, st); break;
+        }
+    } else {
+        assemble_kernel<<<dim3(tiles, W), 256, 0, st>>>(c->S, a);
+    }
     LAUNCH_CHECK();
     return 0;
 }

@@ -199,6 +199,193 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fast path of the likelihood assembly: every node kernel is SquaredExponential / Periodic /
+// QuasiPeriodic (value exp(a s^2 + c r^2), s = sin(pi r / P)) and every weight is Constant or
+// SquaredExponential (value w^2 exp(cw r^2)), so  W_ij F_j = w_ij^2 exp(a_j s_j^2 + (c_j + cw_ij) r^2):
+// one exponential per node (Constant weights: shared by all series) or per (series, node).
+// The sine comes from per-tile angle-addition tables, the exponential from a branch-free
+// polynomial (arguments are <= 0 here).  Same output layout as assemble_kernel (lower block
+// triangle, padding = identity); P = number of series (compile time), WSE = some weight is SE.
+// ---------------------------------------------------------------------------------------------
+#define ASMF_MAXQ 4
+
+// e^x for x <= 0 (NaN propagates, x < -708 flushes to 0): 2^k * Taylor-13(r), |r| <= ln2/2
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;             // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);           // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);          // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);          // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);         // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);           // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);          // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);          // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);         // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);         // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double scale = __hiloint2double((k + 1023) << 20, 0);
+    return (x < -708.0) ? 0.0 : p * scale;
+}
+
+template <int P, bool WSE, bool EDGE>
+__device__ __forceinline__ void asm_fast_rows(const AsmArgs& g, int q, int w, int bi, int bj, int i0, int j0,
+                                              const double (*s_a)[2], const double (*s_amp)[ASMF_MAXQ],
+                                              const double (*s_cs)[ASMF_MAXQ], const double (*s_rowt)[2][ASM_TILE],
+                                              const double (*s_colt)[2][ASM_TILE], const double* s_ta, const double* s_tb,
+                                              const double (*s_diag)[ASM_TILE], double (&chk)[P]) {
+    const int tid = threadIdx.x;
+    const int tx = tid & 63, ty = tid >> 6;
+    const int c0 = 2 * tx;
+    const double tb0 = s_tb[c0], tb1 = s_tb[c0 + 1];
+    const int gj0 = j0 + c0;
+    for (int rr = 0; rr < ASM_TILE / 4; ++rr) {
+        const int row = ty + 4 * rr;
+        const int gi = i0 + row;
+        const double t1 = s_ta[row];
+        const double r0 = t1 - tb0, r1 = t1 - tb1;
+        const double rr0 = r0 * r0, rr1 = r1 * r1;
+        double v0[P], v1[P];
+#pragma unroll
+        for (int s = 0; s < P; ++s) v0[s] = v1[s] = 0.0;
+        for (int j = 0; j < q; ++j) {
+            const double sr = s_rowt[j][0][row], cr = s_rowt[j][1][row];
+            const double2 sc = *reinterpret_cast<const double2*>(&s_colt[j][0][c0]);
+            const double2 cc = *reinterpret_cast<const double2*>(&s_colt[j][1][c0]);
+            const double s0 = fma(sr, cc.x, -cr * sc.x), s1 = fma(sr, cc.y, -cr * sc.y);
+            const double a = s_a[j][0];
+            const double q0 = a * s0 * s0, q1 = a * s1 * s1;
+            if (!WSE) {
+                const double c = s_a[j][1];
+                const double e0 = exp_nonpos(fma(c, rr0, q0)), e1 = exp_nonpos(fma(c, rr1, q1));
+#pragma unroll
+                for (int s = 0; s < P; ++s) {
+                    v0[s] = fma(s_amp[s][j], e0, v0[s]);
+                    v1[s] = fma(s_amp[s][j], e1, v1[s]);
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < P; ++s) {
+                    const double c = s_cs[s][j];
+                    v0[s] = fma(s_amp[s][j], exp_nonpos(fma(c, rr0, q0)), v0[s]);
+                    v1[s] = fma(s_amp[s][j], exp_nonpos(fma(c, rr1, q1)), v1[s]);
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+            double a0 = v0[s], a1 = v1[s];
+            if (EDGE) {
+                if (bi == bj) {
+                    if (gi == gj0) a0 += s_diag[s][row];
+                    if (gi == gj0 + 1) a1 += s_diag[s][row];
+                }
+                const bool in0 = (gi < g.na) && (gj0 < g.nb), in1 = (gi < g.na) && (gj0 + 1 < g.nb);
+                if (!in0) a0 = (gi == gj0) ? 1.0 : 0.0;
+                if (!in1) a1 = (gi == gj0 + 1) ? 1.0 : 0.0;
+            }
+            chk[s] += a0 + a1;
+            double* dst = g.out + (size_t)((size_t)w * P + s) * g.mat_stride + (size_t)gi * g.ld + gj0;
+            *reinterpret_cast<double2*>(dst) = make_double2(a0, a1);
+        }
+    }
+}
+
+template <int P, bool WSE>
+__global__ void __launch_bounds__(256, 2) assemble_fast_kernel(const __grid_constant__ Structure S, const AsmArgs g) {
+    __shared__ double s_a[ASMF_MAXQ][2];                       // a_j, c_j
+    __shared__ double s_b[ASMF_MAXQ];                          // pi / P_j (0: no sine term)
+    __shared__ double s_amp[AGPN_MAXP][ASMF_MAXQ];             // w_ij^2
+    __shared__ double s_cs[AGPN_MAXP][ASMF_MAXQ];              // c_j + cw_ij
+    __shared__ double s_ta[ASM_TILE], s_tb[ASM_TILE];
+    __shared__ double s_diag[AGPN_MAXP][ASM_TILE];
+    __shared__ __align__(16) double s_rowt[ASMF_MAXQ][2][ASM_TILE];   // sin, cos of b (t_row - t0)
+    __shared__ __align__(16) double s_colt[ASMF_MAXQ][2][ASM_TILE];   // sin, cos of b (t_col - t0)
+
+    const int tid = threadIdx.x;
+    const int w = blockIdx.y;
+    const int q = S.q;
+    const int t = blockIdx.x;
+    int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    while (bi * (bi + 1) / 2 > t) --bi;
+    const int bj = t - bi * (bi + 1) / 2;
+    const int i0 = bi * ASM_TILE, j0 = bj * ASM_TILE;
+    const double* th = g.theta + (size_t)w * S.D;
+
+    if (tid < q) {
+        const PKern k = prep_kernel(0, S.node_kind[tid], th + S.node_off[tid]);
+        s_a[tid][0] = (k.kind == K_SE) ? 0.0 : k.a;
+        s_a[tid][1] = (k.kind == K_SE) ? k.a : k.c;            // SE keeps its -1/(2 ell^2) in .a
+        s_b[tid] = (k.kind == K_SE) ? 0.0 : k.b;
+    }
+    __syncthreads();
+    if (tid >= 32 && tid < 32 + P * q) {
+        const int u = tid - 32;
+        const int s = u / q, j = u % q;
+        const int widx = j + q * (g.series0 + s);
+        const PKern k = prep_kernel(1, S.weight_kind[widx], th + S.weight_off[widx]);
+        s_amp[s][j] = k.amp;
+        s_cs[s][j] = s_a[j][1] + ((k.kind == K_SE) ? k.a : 0.0);
+    }
+    if (tid < ASM_TILE) {
+        const int gi = i0 + tid;
+        s_ta[tid] = g.ta[gi < g.na ? gi : g.na - 1];
+    } else {
+        const int gj = j0 + tid - ASM_TILE;
+        s_tb[tid - ASM_TILE] = g.tb[gj < g.nb ? gj : g.nb - 1];
+    }
+    if (bi == bj) {
+        for (int u = tid; u < P * ASM_TILE; u += 256) {
+            const int s = u / ASM_TILE, r = u % ASM_TILE;
+            const int gi = i0 + r;
+            double v = 0.0;
+            if (gi < g.na) {
+                const double e = g.yerr[(size_t)(g.series0 + s) * g.na + gi];
+                const double jt = th[S.jit_off + g.series0 + s];
+                v = e * e + jt * jt;
+            }
+            s_diag[s][r] = v;
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < q; ++j) {
+        const double b = s_b[j];
+        double sv, cv;
+        if (tid < ASM_TILE) {
+            sincos(b * (s_ta[tid] - g.torigin), &sv, &cv);
+            s_rowt[j][0][tid] = sv;
+            s_rowt[j][1][tid] = cv;
+        } else {
+            sincos(b * (s_tb[tid - ASM_TILE] - g.torigin), &sv, &cv);
+            s_colt[j][0][tid - ASM_TILE] = sv;
+            s_colt[j][1][tid - ASM_TILE] = cv;
+        }
+    }
+    __syncthreads();
+
+    double chk[P];
+#pragma unroll
+    for (int s = 0; s < P; ++s) chk[s] = 0.0;
+    const bool edge = (bi == bj) || (i0 + ASM_TILE > g.na) || (j0 + ASM_TILE > g.nb);
+    if (edge)
+        asm_fast_rows<P, WSE, true>(g, q, w, bi, bj, i0, j0, s_a, s_amp, s_cs, s_rowt, s_colt, s_ta, s_tb, s_diag, chk);
+    else
+        asm_fast_rows<P, WSE, false>(g, q, w, bi, bj, i0, j0, s_a, s_amp, s_cs, s_rowt, s_colt, s_ta, s_tb, s_diag, chk);
+    if (g.kflag != nullptr) {
+#pragma unroll
+        for (int s = 0; s < P; ++s)
+            if (!isfinite(chk[s])) g.kflag[(size_t)w * P + s] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct MeanArgs {
     const double* theta;   // [W][D]
     const double* t;       // [n]

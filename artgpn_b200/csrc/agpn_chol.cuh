@@ -75,19 +75,20 @@ __device__ __forceinline__ int swz(int row, int k) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gemm_load_stage(double* stage, const double* __restrict__ Ag, int lda,
                                                 const double* __restrict__ Bg, int ldb, int kc, int tid) {
+    constexpr int CPR = GEMM_KC / 2;                 // 16-byte chunks per operand row
+    constexpr int A_ITERS = TB * CPR / 256, B_ITERS = BN * CPR / 256;
 #pragma unroll
-    for (int u = 0; u < 6; ++u) {
+    for (int u = 0; u < A_ITERS; ++u) {
         const int idx = tid + 256 * u;
-        if (u < 4) {
-            const int row = idx >> 3, ch = idx & 7;
-            cp_async16(stage + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1),
-                       Ag + (size_t)row * lda + kc * GEMM_KC + ch * 2);
-        } else {
-            const int rem = idx - 1024;
-            const int row = rem >> 3, ch = rem & 7;
-            cp_async16(stage + TB * GEMM_KC + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1),
-                       Bg + (size_t)row * ldb + kc * GEMM_KC + ch * 2);
-        }
+        const int row = idx / CPR, ch = idx % CPR;
+        cp_async16(stage + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1), Ag + (size_t)row * lda + kc * GEMM_KC + ch * 2);
+    }
+#pragma unroll
+    for (int u = 0; u < B_ITERS; ++u) {
+        const int idx = tid + 256 * u;
+        const int row = idx / CPR, ch = idx % CPR;
+        cp_async16(stage + TB * GEMM_KC + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1),
+                   Bg + (size_t)row * ldb + kc * GEMM_KC + ch * 2);
     }
 }
 
@@ -111,23 +112,31 @@ __device__ __forceinline__ void gemm_compute_stage(const double* stage, double (
     }
 }
 
-// K must be a multiple of GEMM_KC.  All 256 threads must call.  `active` = this warp issues the
-// tensor work (warps whose output is not needed still take part in the loads and barriers).
-// On return every cp.async issued here has completed and been consumed (safe to overwrite global
-// A / reuse smem after the trailing barrier).
-__device__ __forceinline__ void gemm_nt_tile(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
-                                             int K, double (&acc)[4][4][2], double* smem, bool active = true) {
+// K must be a multiple of GEMM_KC.  All 256 threads must call both halves.  `active` = this warp
+// issues the tensor work (warps whose output is not needed still take part in the loads and
+// barriers).  gemm_nt_prologue only ISSUES the first pipeline stages, so the caller can put its own
+// global loads (the C tile) in flight behind them before anything waits.  When gemm_nt_mainloop
+// returns every cp.async issued here has completed and been consumed (safe to overwrite global A /
+// reuse smem after the trailing barrier).
+__device__ __forceinline__ void gemm_nt_prologue(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
+                                                 int K, double* smem) {
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int wm = warp >> 1;
-    const int wn = warp & 1;
     const int nch = K / GEMM_KC;
 #pragma unroll
     for (int s = 0; s < GEMM_STAGES - 1; ++s) {
         if (s < nch) gemm_load_stage(smem + s * GEMM_STAGE_DOUBLES, Ag, lda, Bg, ldb, s, tid);
         cp_async_commit();
     }
+}
+
+__device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
+                                                 int K, double (&acc)[4][4][2], double* smem, bool active = true) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int wm = warp >> 1;
+    const int wn = warp & 1;
+    const int nch = K / GEMM_KC;
     for (int kc = 0; kc < nch; ++kc) {
         cp_async_wait<GEMM_STAGES - 2>();
         __syncthreads();
@@ -138,6 +147,12 @@ __device__ __forceinline__ void gemm_nt_tile(const double* __restrict__ Ag, int 
     }
     cp_async_wait<0>();
     __syncthreads();
+}
+
+__device__ __forceinline__ void gemm_nt_tile(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
+                                             int K, double (&acc)[4][4][2], double* smem, bool active = true) {
+    gemm_nt_prologue(Ag, lda, Bg, ldb, K, smem);
+    gemm_nt_mainloop(Ag, lda, Bg, ldb, K, acc, smem, active);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -176,6 +191,8 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
     // right half of a diagonal tile: rows 0..63 lie strictly above the diagonal, never read
     const bool active = !(bi == bj && h == 1 && wm < 2);
     double acc[4][4][2];
+    // operand pipeline first, the C tile loads go in flight behind it
+    gemm_nt_prologue(Ai, ld, Aj, ld, depth * TB, smem);
     // acc = -C, so that -(acc + A B^T) = C - A B^T
     if (active) {
 #pragma unroll
@@ -189,7 +206,7 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
                 acc[mi][ni][1] = -c.y;
             }
     }
-    gemm_nt_tile(Ai, ld, Aj, ld, depth * TB, acc, smem, active);
+    gemm_nt_mainloop(Ai, ld, Aj, ld, depth * TB, acc, smem, active);
     if (active) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -281,6 +298,74 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k) {
 #define POTRF_SMEM_DOUBLES (TB * PD_LD + 3 * TB + 8 * 16 * PD_DV_LD + 8 * 16 * PD_DV_LD)
 #define POTRF_SMEM_BYTES (POTRF_SMEM_DOUBLES * 8)
 
+// 16 x 16 diagonal block of panel pb, one warp: lane r (and its mirror r + 16) owns row r in
+// registers.  Per column the UNSCALED column is published once through shared memory; every lane
+// reads the pivot and the entries it needs back as broadcasts, so the serial chain per column is
+// one shared-memory round trip + rsqrt + two multiplies + one fma.
+__device__ __forceinline__ void potrf16_warp(double* S, double* invd, double* ub, int c0, int lane, int* s_fail) {
+    const int r = lane & 15;
+    double d[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) d[c] = S[(c0 + r) * 132 + c0 + c];
+    double myrs = 1.0;
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        double* u = ub + (j & 1) * 16;
+        u[r] = d[j];
+        __syncwarp();
+        double piv = u[j];
+        if (!(piv > 0.0) || isinf(piv)) {          // LAPACK dpotrf: ajj <= 0 or NaN -> not PD
+            bad = 1;
+            piv = 1.0;
+        }
+        const double rs = rsqrt(piv);              // <= 1 ulp; keeps the serial chain short
+        const double t = d[j] * (rs * rs);
+#pragma unroll
+        for (int c = j + 1; c < 16; ++c) d[c] = fma(-t, u[c], d[c]);
+        d[j] = (j == r) ? piv * rs : d[j] * rs;
+        if (j == r) myrs = rs;
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            if (c <= r) S[(c0 + r) * 132 + c0 + c] = d[c];
+        invd[c0 + r] = myrs;
+    }
+    if (bad && lane == 0) *s_fail = 1;
+}
+
+// rank-16 update of one 16 x 16 block (rows r0.., cols q0..) with panel columns c0..c0+15, one warp
+__device__ __forceinline__ void potrf_block_update(double* S, int r0, int q0, int c0, int lane) {
+    double acc[2][2][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+            const double2 c = *reinterpret_cast<const double2*>(S + (r0 + 8 * mi + (lane >> 2)) * 132 + q0 + 8 * ni + 2 * (lane & 3));
+            acc[mi][ni][0] = c.x;
+            acc[mi][ni][1] = c.y;
+        }
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+        double a[2], b[2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) a[mi] = -S[(r0 + 8 * mi + (lane >> 2)) * 132 + c0 + 4 * k4 + (lane & 3)];
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) b[ni] = S[(q0 + 8 * ni + (lane >> 2)) * 132 + c0 + 4 * k4 + (lane & 3)];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+            *reinterpret_cast<double2*>(S + (r0 + 8 * mi + (lane >> 2)) * 132 + q0 + 8 * ni + 2 * (lane & 3)) =
+                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+}
+
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
     extern __shared__ __align__(16) double smem[];
     double* S = smem;                          // [128][132]: lower = A -> L ; strict upper = Linv^T
@@ -298,50 +383,36 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
     double* rhs = g.rhs ? g.rhs + (size_t)mat * ((size_t)g.nblk * TB) + (size_t)k * TB : nullptr;
     if (tid == 0) s_fail = 0;
 
-    // ---- load the lower triangle (coalesced rows; 2 rows per pass) --------------------------------
-    for (int i = tid >> 7; i < TB; i += 2) {
-        const int c = tid & 127;
-        S[i * PD_LD + c] = (c <= i) ? Akk[(size_t)i * ld + c] : 0.0;
+    // ---- load the tile: warp w takes rows 16 w .. 16 w + 15, all 32 loads of a thread in flight ------
+    {
+        double2 v[16][2];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const double* src = Akk + (size_t)(warp * 16 + it) * ld;
+            v[it][0] = *reinterpret_cast<const double2*>(src + 2 * lane);
+            v[it][1] = *reinterpret_cast<const double2*>(src + 64 + 2 * lane);
+        }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int i = warp * 16 + it;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int c = hh * 64 + 2 * lane;
+                double2 o = v[it][hh];
+                if (c > i) o.x = 0.0;
+                if (c + 1 > i) o.y = 0.0;
+                *reinterpret_cast<double2*>(S + i * PD_LD + c) = o;
+            }
+        }
     }
     if (rhs != nullptr && tid < TB) zs[tid] = rhs[tid];
     __syncthreads();
 
-    // ---- factor ---------------------------------------------------------------------------------
+    // ---- factor: panels of 16 columns; the diagonal block of panel pb+1 (serial, one warp) is
+    //      factorised while the other warps apply panel pb to the rest of the trailing matrix --------
+    if (warp == 0) potrf16_warp(S, invd, scr, 0, lane, &s_fail);
     for (int pb = 0; pb < 8; ++pb) {
         const int c0 = pb * 16;
-        if (warp == 0) {
-            // A: 16 x 16 diagonal block, lane r (and its mirror r + 16) owns row r
-            const int r = lane & 15;
-            double d[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) d[c] = S[(c0 + r) * PD_LD + c0 + c];
-            double myrs = 1.0;
-            int bad = 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                double piv = __shfl_sync(0xffffffffu, d[j], j, 16);
-                if (!(piv > 0.0) || isinf(piv)) {      // LAPACK dpotrf: ajj <= 0 or NaN -> not PD
-                    bad = 1;
-                    piv = 1.0;
-                }
-                const double rs = rsqrt(piv);            // <= 1 ulp; keeps the serial chain short
-                if (j == r) myrs = rs;
-                const double l = (j == r) ? sqrt(piv) : d[j] * rs;
-                d[j] = l;
-#pragma unroll
-                for (int c = j + 1; c < 16; ++c) {
-                    const double lc = __shfl_sync(0xffffffffu, l, c, 16);
-                    d[c] = fma(-l, lc, d[c]);
-                }
-            }
-            if (lane < 16) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c)
-                    if (c <= r) S[(c0 + r) * PD_LD + c0 + c] = d[c];
-                invd[c0 + r] = myrs;
-            }
-            if (bad && lane == 0) s_fail = 1;
-        }
         __syncthreads();
         // B: rows below the diagonal block, one thread per row: x L_D^T = b
         const int nrows = TB - c0 - 16;
@@ -359,45 +430,23 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
             for (int j = 0; j < 16; ++j) rowp[j] = x[j];
         }
         __syncthreads();
-        // C: trailing blocks (bi >= bj > pb) -= X_bi X_bj^T, one 16 x 16 block per warp and pass
+        if (pb == 7) break;
+        // C: trailing blocks (bi >= bj > pb) -= X_bi X_bj^T
         const int nb = 7 - pb;
         const int nblocks = nb * (nb + 1) / 2;
-        for (int t = warp; t < nblocks; t += 8) {
-            int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-            while (bi * (bi + 1) / 2 > t) --bi;
-            const int bj = t - bi * (bi + 1) / 2;
-            const int r0 = (pb + 1 + bi) * 16, q0 = (pb + 1 + bj) * 16;
-            double acc[2][2][2];
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni) {
-                    const double2 c = *reinterpret_cast<const double2*>(
-                        S + (r0 + 8 * mi + (lane >> 2)) * PD_LD + q0 + 8 * ni + 2 * (lane & 3));
-                    acc[mi][ni][0] = c.x;
-                    acc[mi][ni][1] = c.y;
-                }
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                double a[2], b[2];
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi) a[mi] = -S[(r0 + 8 * mi + (lane >> 2)) * PD_LD + c0 + 4 * k4 + (lane & 3)];
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni) b[ni] = S[(q0 + 8 * ni + (lane >> 2)) * PD_LD + c0 + 4 * k4 + (lane & 3)];
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        if (warp == 0) {
+            potrf_block_update(S, c0 + 16, c0 + 16, c0, lane);      // next diagonal block first ...
+            __syncwarp();
+            potrf16_warp(S, invd, scr, c0 + 16, lane, &s_fail);    // ... and factor it right away
+        } else {
+            for (int t = warp; t < nblocks; t += 7) {
+                int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+                while (bi * (bi + 1) / 2 > t) --bi;
+                const int bj = t - bi * (bi + 1) / 2;
+                potrf_block_update(S, (pb + 1 + bi) * 16, (pb + 1 + bj) * 16, c0, lane);
             }
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni)
-                    *reinterpret_cast<double2*>(S + (r0 + 8 * mi + (lane >> 2)) * PD_LD + q0 + 8 * ni + 2 * (lane & 3)) =
-                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
-        __syncthreads();
     }
 
     // ---- write L back (lower triangle incl. diagonal) -----------------------------------------------
@@ -424,15 +473,20 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
         }
     }
     __syncthreads();
-    // ---- inverse, step 2: block rows i = 1..7:  X_ij = -Dinv_i * sum_{m=j}^{i-1} L_im X_mj  (warp j) --
-    for (int i = 1; i < 8; ++i) {
-        if (warp < i) {
-            const int j = warp;
-            double acc[2][2][2];
+    // ---- inverse, step 2: warp j owns block column j of X = L^-1 and walks down the block rows:
+    //      X_ij = -Dinv_i * sum_{m=j}^{i-1} L_im X_mj.  No block-wide barrier: a warp only reads
+    //      the X blocks it produced itself.  Four accumulator sets keep the DMMA chains short. -------
+    {
+        const int j = warp;
+        double* sc = scr + warp * 16 * PD_DV_LD;
+        for (int i = j + 1; i < 8; ++i) {
+            double acc[4][2][2][2];
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) acc[u][mi][ni][0] = acc[u][mi][ni][1] = 0.0;
             for (int m = j; m < i; ++m) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
@@ -449,21 +503,24 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                        for (int ni = 0; ni < 2; ++ni) dmma884(acc[k4][mi][ni][0], acc[k4][mi][ni][1], a[mi], b[ni]);
                 }
             }
             // P -> per-warp scratch (as a B operand: [k][n]), then Y = -Dinv_i P
-            double* sc = scr + warp * 16 * PD_DV_LD;
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {
                     const int rr = 8 * mi + (lane >> 2), cc = 8 * ni + 2 * (lane & 3);
-                    sc[rr * PD_DV_LD + cc] = acc[mi][ni][0];
-                    sc[rr * PD_DV_LD + cc + 1] = acc[mi][ni][1];
-                    acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                    sc[rr * PD_DV_LD + cc] = (acc[0][mi][ni][0] + acc[1][mi][ni][0]) + (acc[2][mi][ni][0] + acc[3][mi][ni][0]);
+                    sc[rr * PD_DV_LD + cc + 1] = (acc[0][mi][ni][1] + acc[1][mi][ni][1]) + (acc[2][mi][ni][1] + acc[3][mi][ni][1]);
                 }
             __syncwarp();
+            double y[2][2][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) y[mi][ni][0] = y[mi][ni][1] = 0.0;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
                 double a[2], b[2];
@@ -475,7 +532,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    for (int ni = 0; ni < 2; ++ni) dmma884(y[mi][ni][0], y[mi][ni][1], a[mi], b[ni]);
             }
             // X_ij[r][c] -> transposed into the upper triangle: S[16 j + c][16 i + r]
 #pragma unroll
@@ -483,13 +540,13 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {
                     const int rr = 8 * mi + (lane >> 2), cc = 8 * ni + 2 * (lane & 3);
-                    S[(16 * j + cc) * PD_LD + 16 * i + rr] = acc[mi][ni][0];
-                    S[(16 * j + cc + 1) * PD_LD + 16 * i + rr] = acc[mi][ni][1];
+                    S[(16 * j + cc) * PD_LD + 16 * i + rr] = y[mi][ni][0];
+                    S[(16 * j + cc + 1) * PD_LD + 16 * i + rr] = y[mi][ni][1];
                 }
             __syncwarp();
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- write the inverse (full tile, zeros above the diagonal) -------------------------------------
     double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
