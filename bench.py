@@ -190,6 +190,10 @@ def main():
         return 0
 
     # ---------------------------------------------------------------- B200 arm
+    # Libraries (NCCL prints its version banner) may write to stdout: keep fd 1 for the JSON line only.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process; bounded sample (one eval per host core)
@@ -346,7 +350,8 @@ def main():
                                             "n": int(len(ref_vals)), "tolerance": 1e-9}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
