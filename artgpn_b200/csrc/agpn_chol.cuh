@@ -112,25 +112,86 @@ __device__ __forceinline__ void gemm_compute_stage(const double* stage, double (
     }
 }
 
-// K must be a multiple of GEMM_KC.  All 256 threads must call both halves.  `active` = this warp
-// issues the tensor work (warps whose output is not needed still take part in the loads and
-// barriers).  gemm_nt_prologue only ISSUES the first pipeline stages, so the caller can put its own
-// global loads (the C tile) in flight behind them before anything waits.  When gemm_nt_mainloop
-// returns every cp.async issued here has completed and been consumed (safe to overwrite global A /
-// reuse smem after the trailing barrier).
-__device__ __forceinline__ void gemm_nt_prologue(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
-                                                 int K, double* smem) {
-    const int tid = threadIdx.x;
-    const int nch = K / GEMM_KC;
-#pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; ++s) {
-        if (s < nch) gemm_load_stage(smem + s * GEMM_STAGE_DOUBLES, Ag, lda, Bg, ldb, s, tid);
-        cp_async_commit();
+// ---- mbarrier-decoupled cp.async pipeline ----------------------------------------------------------
+// A CTA-wide __syncthreads per k-chunk makes every warp wait for the slowest one (14 % of warp time
+// in the K = 512 update, ncu r01c).  Instead each stage has two mbarriers:
+//   full[s]   256 arrivals: every thread's cp.async group for that stage signals it on completion
+//             (cp.async.mbarrier.arrive.noinc) -> a warp waits only for the DATA;
+//   empty[s]  8 arrivals: one per warp after its last read of the stage -> a stage is refilled only
+//             when all warps are done with it, checked one chunk later than needed (slack).
+// `g` counts chunks over the whole kernel so the phase parities stay consistent across several GEMMs.
+struct GemmPipe {
+    unsigned full;    // shared-space address of full[GEMM_STAGES]
+    unsigned empty;   // shared-space address of empty[GEMM_STAGES]
+    unsigned g;       // chunks consumed so far by this thread (identical in all threads)
+};
+
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(addr), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive(unsigned addr) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+    unsigned done = 0;
+    unsigned spins = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();     // a protocol bug must fault, not hang the GPU
     }
 }
 
-__device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
-                                                 int K, double (&acc)[4][4][2], double* smem, bool active = true) {
+// call once per kernel by all 256 threads, before the first GEMM; bars = 2 * GEMM_STAGES uint64_t in shared
+__device__ __forceinline__ GemmPipe gemm_pipe_init(unsigned long long* bars) {
+    GemmPipe p;
+    p.full = (unsigned)__cvta_generic_to_shared(bars);
+    p.empty = p.full + 8 * GEMM_STAGES;
+    p.g = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < GEMM_STAGES; ++s) {
+            mbar_init(p.full + 8 * s, 256);
+            mbar_init(p.empty + 8 * s, 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    return p;
+}
+
+// issue the loads of local chunk `c` (global chunk index p.g + c) into its stage
+__device__ __forceinline__ void gemm_issue_chunk(const GemmPipe& p, int c, const double* __restrict__ Ag, int lda,
+                                                 const double* __restrict__ Bg, int ldb, double* smem, int tid) {
+    const unsigned n = p.g + c;
+    const unsigned s = n % GEMM_STAGES;
+    if (n >= GEMM_STAGES) mbar_wait(p.empty + 8 * s, ((n / GEMM_STAGES) - 1) & 1);
+    gemm_load_stage(smem + s * GEMM_STAGE_DOUBLES, Ag, lda, Bg, ldb, c, tid);
+    mbar_cp_async_arrive(p.full + 8 * s);
+}
+
+// K must be a multiple of GEMM_KC.  All 256 threads must call both halves.  `active` = this warp
+// issues the tensor work (warps whose output is not needed still take part in the loads and the
+// barriers).  gemm_nt_prologue only ISSUES the first pipeline stages, so the caller can put its own
+// global loads (the C tile) in flight behind them before anything waits.  When gemm_nt_mainloop
+// returns, every cp.async issued by ANY thread of the CTA for this GEMM has completed (the last
+// full-barrier needs all 256 arrivals), so global operands may be overwritten; shared memory may
+// still be read by slower warps -- callers that reuse it by other means need their own barrier.
+__device__ __forceinline__ void gemm_nt_prologue(const GemmPipe& p, const double* __restrict__ Ag, int lda,
+                                                 const double* __restrict__ Bg, int ldb, int K, double* smem) {
+    const int tid = threadIdx.x;
+    const int nch = K / GEMM_KC;
+#pragma unroll
+    for (int c = 0; c < GEMM_STAGES - 1; ++c)
+        if (c < nch) gemm_issue_chunk(p, c, Ag, lda, Bg, ldb, smem, tid);
+}
+
+__device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __restrict__ Ag, int lda,
+                                                 const double* __restrict__ Bg, int ldb, int K, double (&acc)[4][4][2],
+                                                 double* smem, bool active = true) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -138,21 +199,22 @@ __device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ Ag, 
     const int wn = warp & 1;
     const int nch = K / GEMM_KC;
     for (int kc = 0; kc < nch; ++kc) {
-        cp_async_wait<GEMM_STAGES - 2>();
-        __syncthreads();
+        const unsigned n = p.g + kc;
+        const unsigned s = n % GEMM_STAGES;
+        mbar_wait(p.full + 8 * s, (n / GEMM_STAGES) & 1);
+        if (active) gemm_compute_stage(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p.empty + 8 * s);
         const int nxt = kc + GEMM_STAGES - 1;
-        if (nxt < nch) gemm_load_stage(smem + (nxt % GEMM_STAGES) * GEMM_STAGE_DOUBLES, Ag, lda, Bg, ldb, nxt, tid);
-        cp_async_commit();
-        if (active) gemm_compute_stage(smem + (kc % GEMM_STAGES) * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+        if (nxt < nch) gemm_issue_chunk(p, nxt, Ag, lda, Bg, ldb, smem, tid);
     }
-    cp_async_wait<0>();
-    __syncthreads();
+    p.g += nch;
 }
 
-__device__ __forceinline__ void gemm_nt_tile(const double* __restrict__ Ag, int lda, const double* __restrict__ Bg, int ldb,
-                                             int K, double (&acc)[4][4][2], double* smem, bool active = true) {
-    gemm_nt_prologue(Ag, lda, Bg, ldb, K, smem);
-    gemm_nt_mainloop(Ag, lda, Bg, ldb, K, acc, smem, active);
+__device__ __forceinline__ void gemm_nt_tile(GemmPipe& p, const double* __restrict__ Ag, int lda, const double* __restrict__ Bg,
+                                             int ldb, int K, double (&acc)[4][4][2], double* smem, bool active = true) {
+    gemm_nt_prologue(p, Ag, lda, Bg, ldb, K, smem);
+    gemm_nt_mainloop(p, Ag, lda, Bg, ldb, K, acc, smem, active);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -167,6 +229,8 @@ __device__ __forceinline__ void gemm_nt_tile(const double* __restrict__ Ag, int 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, int depth, int j0, int narrow) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * GEMM_STAGES];
+    GemmPipe pipe = gemm_pipe_init(bars);
     const int t = blockIdx.x >> 1;
     const int h = blockIdx.x & 1;
     int bi, bj;
@@ -192,7 +256,7 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
     const bool active = !(bi == bj && h == 1 && wm < 2);
     double acc[4][4][2];
     // operand pipeline first, the C tile loads go in flight behind it
-    gemm_nt_prologue(Ai, ld, Aj, ld, depth * TB, smem);
+    gemm_nt_prologue(pipe, Ai, ld, Aj, ld, depth * TB, smem);
     // acc = -C, so that -(acc + A B^T) = C - A B^T
     if (active) {
 #pragma unroll
@@ -206,7 +270,7 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
                 acc[mi][ni][1] = -c.y;
             }
     }
-    gemm_nt_mainloop(Ai, ld, Aj, ld, depth * TB, acc, smem, active);
+    gemm_nt_mainloop(pipe, Ai, ld, Aj, ld, depth * TB, acc, smem, active);
     if (active) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -232,6 +296,8 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double zs[TB];
     __shared__ double red[2][TB];
+    __shared__ __align__(8) unsigned long long bars[2 * GEMM_STAGES];
+    GemmPipe pipe = gemm_pipe_init(bars);
     const int ti = k + 1 + blockIdx.x;
     const int mat = blockIdx.y;
     double* A = g.A + (size_t)mat * g.mat_stride;
@@ -243,6 +309,7 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     if (rhs != nullptr && tid < TB) zs[tid] = rhs[(size_t)k * TB + tid];
+    __syncthreads();
     double part[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][4][2];
 #pragma unroll
@@ -252,8 +319,8 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k) {
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        gemm_nt_tile(Aik, ld, Linv + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem);
-        // the gemm ended with a barrier after all of its loads completed: in-place store is safe
+        gemm_nt_tile(pipe, Aik, ld, Linv + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem);
+        // every load of this GEMM (by any thread) has completed: the in-place store is safe
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll

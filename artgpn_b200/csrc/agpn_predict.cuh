@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(256, 2) predict_kernel(const __grid_constant__
     __shared__ PKern s_weight[AGPN_MAXQ];
     __shared__ double s_ts[TB], s_tn[TB], s_z[TB];
     __shared__ double s_red[2][2][TB];
+    __shared__ __align__(8) unsigned long long bars[2 * GEMM_STAGES];
+    GemmPipe pipe = gemm_pipe_init(bars);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256, 2) predict_kernel(const __grid_constant__
                     }
                 }
             }
-            if (k > 0) gemm_nt_tile(Vrow, g.n_pad, g.L + ((size_t)k * TB + h * BN) * g.ld, g.ld, k * TB, acc, smem);
+            if (k > 0) gemm_nt_tile(pipe, Vrow, g.n_pad, g.L + ((size_t)k * TB + h * BN) * g.ld, g.ld, k * TB, acc, smem);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256, 2) predict_kernel(const __grid_constant__
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            gemm_nt_tile(Vt, g.n_pad, g.Linv + (size_t)k * TB * TB + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem);
+            gemm_nt_tile(pipe, Vt, g.n_pad, g.Linv + (size_t)k * TB * TB + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
                 const int row = wm * 32 + mi * 8 + (lane >> 2);
