@@ -1,0 +1,61 @@
+"""Sampler adapter: host bookkeeping on CPU with an injected evaluator,
+end to end on the GPU with the real network."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+def test_stretch_move_samples_a_gaussian():
+    from artgpn_b200.sampler import stretch_move
+    calls = []
+
+    def logp(x):
+        calls.append(x.shape[0])
+        return -0.5 * np.sum((x - 1.0) ** 2 / 0.25, axis=1)
+    rng = np.random.default_rng(0)
+    p0 = 1.0 + 0.1 * rng.normal(size=(16, 3))
+    chain, lp, acc = stretch_move(logp, p0, 600, seed=1)
+    flat = chain[200:].reshape(-1, 3)
+    assert np.allclose(flat.mean(axis=0), 1.0, atol=0.06)
+    assert np.allclose(flat.std(axis=0), 0.5, atol=0.08)
+    assert 0.2 < acc.mean() < 0.9
+    assert set(calls[1:]) == {8}              # every half-step is ONE batched call of W/2 rows
+    assert np.allclose(lp[-1], logp(chain[-1]))
+
+
+@pytest.mark.gpu
+def test_batched_posterior_matches_reference_log_transform_shape():
+    """Sun example (examples/Sun/01_emcee.py:76-108): theta = (n2, n3, n4, w11, w12, w13, s1, off1, s2,
+    off2, s3, off3, j1, j2, j3) -> identity column map; priors cut rows before the GPU call."""
+    from artgpn_b200 import node, weight, mean
+    from artgpn_b200.sampler import BatchedPosterior, run_mcmc
+    case = H.loglike_case("G4_sun50_initial")
+    net = H.product_network(case)
+    nodes, weights, means = H.product_objs(case)
+
+    def log_prior(th):
+        lp = np.zeros(th.shape[0])
+        lp[th[:, 0] < 0.5 * th[:, 1]] = -np.inf          # 01_emcee.py:78-79
+        lp[np.any(th[:, :6] <= 0, axis=1)] = -np.inf
+        return lp
+    post = BatchedPosterior(net, nodes, weights, means, log_prior=log_prior)
+    assert post.ndim == 15
+    base = np.array([10, 20, 0.5, 1, 1, 1, 0, means[0].pars[1], 0, means[1].pars[1], 0, means[2].pars[1]]
+                    + list(case["jitters"]), dtype=float)
+    assert abs(post(base) - case["ll"]) <= 1e-9 * abs(case["ll"])
+    rows = np.tile(base, (4, 1))
+    rows[1, 0] = 5.0                 # violates eta2 >= eta3 / 2 -> prior -inf, not evaluated
+    rows[2, 1] = np.nan              # NaN -> -inf for a sampler
+    before = post.n_evaluated
+    out = post(rows)
+    assert post.n_evaluated - before == 3
+    assert np.isneginf(out[1]) and np.isneginf(out[2])
+    assert abs(out[0] - case["ll"]) <= 1e-9 * abs(case["ll"]) and out[3] == out[0]
+    # fixed entries + column map: sample only the three node parameters
+    post3 = BatchedPosterior(net, nodes, weights, means, columns={0: 0, 1: 1, 2: 2},
+                             fixed={i: base[i] for i in range(3, 15)})
+    assert post3.ndim == 3 and abs(post3(base[:3]) - case["ll"]) <= 1e-9 * abs(case["ll"])
+    rng = np.random.default_rng(3)
+    res = run_mcmc(lambda: base[:3] * (1 + 0.01 * rng.normal(size=3)), post3, iterations=20)
+    assert res.shape == (6 * 10, 4) and np.all(np.isfinite(res))
