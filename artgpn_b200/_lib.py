@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libartgpn_b200.so")
+LIB_PATH = os.environ.get("AGPN_LIB") or os.path.join(_HERE, "libartgpn_b200.so")   # AGPN_LIB: build-variant A/B tests
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)

@@ -10,16 +10,17 @@
 // columns and left-looking inside a group (see run_cholesky in agpn_api.cu): the wide trailing
 // update applies a whole group at once (K = 128 * group).  Three kernels, each over ALL matrices
 // of the batch (grid.y = matrix):
-//   potrf_diag_kernel   one CTA per matrix: 128x128 diagonal block factorised in registers
-//                       (2-D cyclic thread ownership, one column broadcast per step through
-//                       shared memory), its inverse by the same sweep, and -- folded in -- the
-//                       forward-solve block z_k = L_kk^-1 r_k, |z_k|^2 and sum log L_jj
-//                       (warp-shuffle reductions).
+//   potrf_diag_kernel   one CTA per matrix: 128x128 diagonal block factorised in shared memory
+//                       as 8 panels of 16 columns (serial 16x16 block by one warp with look-ahead,
+//                       rank-16 updates on DMMA), its inverse by block forward substitution on
+//                       DMMA, and -- folded in -- the forward-solve block z_k = L_kk^-1 r_k,
+//                       |z_k|^2 and sum log L_jj (warp-shuffle reductions).
 //   trsm_kernel         L_ik = A_ik * L_kk^-T as an NT GEMM with the inverted diagonal block
 //                       on the FP64 tensor pipe (DMMA.8x8x4); also r_i -= L_ik z_k.
 //   syrk_kernel         A_ij -= L_ik L_jk^T for all trailing tiles i >= j > k, DMMA.8x8x4,
-//                       operands staged through a 4-stage cp.async shared-memory pipeline with an
-//                       XOR swizzle that makes the 64-bit fragment loads bank-conflict free.
+//                       operands staged through a 4-stage cp.async shared-memory pipeline whose
+//                       stages are handed over by mbarriers (no CTA-wide barrier per k-chunk), with
+//                       an XOR swizzle that makes the 64-bit fragment loads bank-conflict free.
 //                       CTA tile 128 x 64, two CTAs per SM.
 #pragma once
 #include <cuda_runtime.h>
@@ -27,8 +28,12 @@
 
 #define TB 128                 // tile edge (block column width of the factorisation)
 #define BN 64                  // n extent of one GEMM CTA tile (128 x 64, two CTAs per SM)
+#ifndef GEMM_KC
 #define GEMM_KC 16             // k extent of one pipeline stage
+#endif
+#ifndef GEMM_STAGES
 #define GEMM_STAGES 4
+#endif
 #define GEMM_STAGE_DOUBLES ((TB + BN) * GEMM_KC)
 #define GEMM_SMEM_BYTES (GEMM_STAGES * GEMM_STAGE_DOUBLES * 8)   // 98304
 
@@ -62,8 +67,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // swizzled offset (in doubles) of element (row, k) inside a [rows][16] stage operand: the 16-byte
 // chunk index is XORed with 2*(row & 3), which spreads the 8 rows x 4 k of one DMMA fragment load
 // over all 32 banks (64-bit accesses, two half-warp phases).
+__device__ __forceinline__ int swz_x(int row) {
+#if GEMM_KC >= 16
+    return (row & 3) << 1;             // 128-byte (or longer) rows: 4 rows x 2 chunks -> 8 distinct chunks
+#else
+    return ((row >> 1) & 1) << 1;      // 64-byte rows: two rows share a bank line
+#endif
+}
 __device__ __forceinline__ int swz(int row, int k) {
-    return row * GEMM_KC + ((((k >> 1) ^ ((row & 3) << 1)) << 1) | (k & 1));
+    return row * GEMM_KC + ((((k >> 1) ^ swz_x(row)) << 1) | (k & 1));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -81,13 +93,13 @@ __device__ __forceinline__ void gemm_load_stage(double* stage, const double* __r
     for (int u = 0; u < A_ITERS; ++u) {
         const int idx = tid + 256 * u;
         const int row = idx / CPR, ch = idx % CPR;
-        cp_async16(stage + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1), Ag + (size_t)row * lda + kc * GEMM_KC + ch * 2);
+        cp_async16(stage + row * GEMM_KC + ((ch ^ swz_x(row)) << 1), Ag + (size_t)row * lda + kc * GEMM_KC + ch * 2);
     }
 #pragma unroll
     for (int u = 0; u < B_ITERS; ++u) {
         const int idx = tid + 256 * u;
         const int row = idx / CPR, ch = idx % CPR;
-        cp_async16(stage + TB * GEMM_KC + row * GEMM_KC + ((ch ^ ((row & 3) << 1)) << 1),
+        cp_async16(stage + TB * GEMM_KC + row * GEMM_KC + ((ch ^ swz_x(row)) << 1),
                    Bg + (size_t)row * ldb + kc * GEMM_KC + ch * 2);
     }
 }
@@ -201,12 +213,21 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __re
     for (int kc = 0; kc < nch; ++kc) {
         const unsigned n = p.g + kc;
         const unsigned s = n % GEMM_STAGES;
+#ifdef GEMM_ISSUE_BEFORE
+        const int nxt = kc + GEMM_STAGES - 1;
+        if (nxt < nch) gemm_issue_chunk(p, nxt, Ag, lda, Bg, ldb, smem, tid);
+        mbar_wait(p.full + 8 * s, (n / GEMM_STAGES) & 1);
+        if (active) gemm_compute_stage(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p.empty + 8 * s);
+#else
         mbar_wait(p.full + 8 * s, (n / GEMM_STAGES) & 1);
         if (active) gemm_compute_stage(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(p.empty + 8 * s);
         const int nxt = kc + GEMM_STAGES - 1;
         if (nxt < nch) gemm_issue_chunk(p, nxt, Ag, lda, Bg, ldb, smem, tid);
+#endif
     }
     p.g += nch;
 }
@@ -484,14 +505,17 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
         // B: rows below the diagonal block, one thread per row: x L_D^T = b
         const int nrows = TB - c0 - 16;
         if (tid < nrows) {
+            // right-looking in registers: once x[m] is known all later entries take their update at
+            // once (independent fmas), so the dependent chain is 16 x (mul + fma), not 120 fmas
             double* rowp = S + (c0 + 16 + tid) * PD_LD + c0;
             double x[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                double sacc = rowp[j];
+            for (int j = 0; j < 16; ++j) x[j] = rowp[j];
 #pragma unroll
-                for (int m = 0; m < j; ++m) sacc = fma(-x[m], S[(c0 + j) * PD_LD + c0 + m], sacc);
-                x[j] = sacc * invd[c0 + j];
+            for (int m = 0; m < 16; ++m) {
+                x[m] *= invd[c0 + m];
+#pragma unroll
+                for (int j = m + 1; j < 16; ++j) x[j] = fma(-x[m], S[(c0 + j) * PD_LD + c0 + m], x[j]);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) rowp[j] = x[j];
@@ -528,11 +552,12 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
         const int c = lane & 15;
         double x[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            double sacc = (i == c) ? 1.0 : 0.0;
+        for (int i = 0; i < 16; ++i) x[i] = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-            for (int m = 0; m < i; ++m) sacc = fma(-S[(c0 + i) * PD_LD + c0 + m], x[m], sacc);
-            x[i] = (i >= c) ? sacc * invd[c0 + i] : 0.0;
+        for (int m = 0; m < 16; ++m) {                 // right-looking: short dependent chain
+            x[m] = (m >= c) ? x[m] * invd[c0 + m] : 0.0;
+#pragma unroll
+            for (int i = m + 1; i < 16; ++i) x[i] = fma(-S[(c0 + i) * PD_LD + c0 + m], x[m], x[i]);
         }
         if (lane < 16) {
 #pragma unroll

@@ -122,3 +122,29 @@ def test_torch_device_tensor_path():
     torch.cuda.synchronize()
     assert out.is_cuda and H.rel_err(out.cpu().numpy(), exp) <= LL_RTOL
     assert np.array_equal(out.cpu().numpy(), net.log_likelihood_batch(theta))
+
+
+def test_sharded_entry_point_single_rank_nccl():
+    """log_likelihood_batch_sharded through NCCL with world_size 1 (multi-rank logic: tests/test_sharding_gloo.py)."""
+    import os
+    import socket
+    import torch
+    import torch.distributed as dist
+    from artgpn_b200 import synth, node, weight, mean, sharding
+    b = H.cases()["batch"][0]
+    a = H.arrays()
+    theta, exp = a[b["name"] + "_theta"], a[b["name"] + "_ll"]
+    net = H.product_network(b["data"], b["q"])
+    net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], b["p"], b["q"], b["weights"])[:3])
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        full = sharding.log_likelihood_batch_sharded(net, theta)
+        torch.cuda.synchronize()
+        assert full.is_cuda and H.rel_err(full.cpu().numpy(), exp) <= LL_RTOL
+    finally:
+        dist.destroy_process_group()
