@@ -15,6 +15,7 @@
 #include "agpn_chol.cuh"
 #include "agpn_eval.cuh"
 #include "agpn_predict.cuh"
+#include "agpn_small.cuh"
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
@@ -81,8 +82,10 @@ struct agpn_ctx {
     struct Ev { cudaEvent_t a, b; int ph; };
     std::vector<Ev> evs;
     bool attrs_set = false;
+    size_t small_smem_set = 0;
     int group = 4;             // block columns per wide trailing update (AGPN_GROUP)
     bool no_fast_asm = false;  // AGPN_GENERIC_ASM=1 forces the generic assembly kernel
+    bool no_small = false;     // AGPN_NO_SMALL=1 disables the fused small-N kernel
     // sub-batch streams: the matrices of a batch are split over nsub streams so that one sub-batch's
     // small serial kernels (diagonal block, panel solve) overlap another's wide tensor update
     int nsub = 3;              // AGPN_STREAMS
@@ -133,6 +136,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     c->t0 = time[0];
     if (const char* e = getenv("AGPN_GROUP")) c->group = atoi(e) > 0 ? atoi(e) : 4;
     if (const char* e = getenv("AGPN_GENERIC_ASM")) c->no_fast_asm = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_NO_SMALL")) c->no_small = atoi(e) != 0;
     memset(&c->S, 0, sizeof(Structure));
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_t, sizeof(double) * N)) != cudaSuccess ||
@@ -413,15 +417,19 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
     const int p = c->p, D = c->S.D;
     const size_t np = (size_t)c->npad;
 
-    // walkers per wave: bounded by free memory and by grid.y
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const size_t have = c->cap_mats * np * np * sizeof(double);
-    const size_t per_walker = (size_t)p * (np * np + TB * TB + np) * sizeof(double) + 64;
-    size_t wave = (size_t)((free_b + have) * 0.85) / per_walker;
-    if (wave < 1) USAGE_FAIL("agpn_loglike_batch: not enough device memory for one walker");
-    if (wave > (size_t)W) wave = W;
+    // walkers per wave: bounded by free memory and by grid.y.  cudaMemGetInfo is slow (it can take
+    // milliseconds), so it is only consulted when the workspace has to grow.
+    size_t wave = (size_t)W;
     if (wave * p > 65535) wave = 65535 / p;
+    if (wave * p > c->cap_mats) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t have = c->cap_mats * np * np * sizeof(double);
+        const size_t per_walker = (size_t)p * (np * np + TB * TB + np) * sizeof(double) + 64;
+        const size_t fit = (size_t)((free_b + have) * 0.85) / per_walker;
+        if (fit < 1) USAGE_FAIL("agpn_loglike_batch: not enough device memory for one walker");
+        if (wave > fit) wave = fit;
+    }
     if (ensure_batch_workspace(c, wave * p, wave)) return 1;
 
     for (int ph = 0; ph < PH_COUNT; ++ph) {
@@ -453,6 +461,31 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
             mean_kernel<<<dim3(p, Ww), 256, 0, st>>>(c->S, m);
             LAUNCH_CHECK();
         }
+        const int small_nb = (c->N + 15) / 16;
+        const bool use_small = !c->no_small && small_nb <= SM_MAXNB;
+        if (use_small) {
+            // K0: assembly + factorisation + solve fused in one CTA's shared memory per (walker, series)
+            PhaseScope ps(c, st, PH_ASM, cur);
+            AsmArgs probe;
+            probe.lower_only = 1; probe.square = 1; probe.add_err = 1; probe.add_jit = 1; probe.pad_identity = 1; probe.vec2 = 1;
+            probe.nser = 1; probe.rows_out = c->npad; probe.cols_out = c->npad; probe.series0 = 0;
+            bool wse = false, fast = true;
+            for (int s = 0; s < p && fast; ++s) {
+                probe.series0 = s;
+                fast = fast_assembly_ok(c, probe, &wse);
+            }
+            SmallArgs sa;
+            sa.theta = d_theta; sa.t = c->d_t; sa.yerr = c->d_yerr; sa.rhs = c->d_rhs; sa.rhs_stride = c->npad;
+            sa.N = c->N; sa.nb = small_nb; sa.fast = fast ? 1 : 0; sa.torigin = c->t0;
+            sa.logdet = c->d_logdet; sa.quad = c->d_quad; sa.info = d_infoflag; sa.kflag = d_kflag;
+            const size_t smem = small_smem_bytes(small_nb, c->q);
+            if (smem > c->small_smem_set) {
+                CUDA_TRY(cudaFuncSetAttribute(small_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                c->small_smem_set = smem;
+            }
+            small_fused_kernel<<<dim3(p, Ww), 256, smem, st>>>(c->S, sa);
+            LAUNCH_CHECK();
+        } else {
         {
             PhaseScope ps(c, st, PH_ASM, cur);
             AsmArgs a;
@@ -490,6 +523,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
                 CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[si], 0));
             }
         }
+        }   // !use_small
         double* d_out = out_on_device ? out + w0 : c->d_out;
         {
             PhaseScope ps(c, st, PH_FINAL, cur);

@@ -10,8 +10,19 @@ pytestmark = pytest.mark.gpu
 LL_RTOL = 1e-9
 
 
+@pytest.fixture(params=["fused_small", "tiled"])
+def path(request, monkeypatch):
+    """N <= 192 normally takes the fused single-CTA kernel (K0); AGPN_NO_SMALL=1 (read when the context
+    is created) forces the tiled assembly + blocked Cholesky path so both are checked on every case."""
+    if request.param == "tiled":
+        monkeypatch.setenv("AGPN_NO_SMALL", "1")
+    else:
+        monkeypatch.delenv("AGPN_NO_SMALL", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("case", H.cases()["loglike"], ids=lambda c: c["name"])
-def test_loglike_vs_reference_goldens(case):
+def test_loglike_vs_reference_goldens(case, path):
     net = H.product_network(case)
     nodes, weights, means = H.product_objs(case)
     exp = case["ll"]
@@ -26,7 +37,7 @@ def test_loglike_vs_reference_goldens(case):
 
 
 @pytest.mark.parametrize("b", H.cases()["batch"], ids=lambda c: c["name"])
-def test_batch_vs_reference_goldens(b):
+def test_batch_vs_reference_goldens(b, path):
     from artgpn_b200 import synth, node, weight, mean
     a = H.arrays()
     theta, exp = a[b["name"] + "_theta"], a[b["name"] + "_ll"]
@@ -45,8 +56,8 @@ def test_batch_vs_reference_goldens(b):
     assert one == got[0]
 
 
-@pytest.mark.parametrize("N", [1, 2, 20, 127, 128, 129, 255, 256, 300])
-def test_ragged_sizes_vs_oracle(N):
+@pytest.mark.parametrize("N", [1, 2, 15, 16, 17, 20, 127, 128, 129, 191, 192, 193, 255, 256, 300])
+def test_ragged_sizes_vs_oracle(N, path):
     from artgpn_b200 import synth, node, weight, mean
     from artgpn_b200.arttwo import network
     t, y, sig = synth.make_data(N, 2, seed=10 + N)
@@ -66,7 +77,7 @@ def test_ragged_sizes_vs_oracle(N):
         assert abs(got[w] - exp) <= LL_RTOL * abs(exp), (N, w, got[w], exp)
 
 
-def test_batch_status_and_mixed_failures():
+def test_batch_status_and_mixed_failures(path):
     """-inf / NaN rows inside a batch do not disturb their neighbours (arttwo.py:288-289)."""
     from artgpn_b200 import synth, node, weight, mean
     b = H.cases()["batch"][0]
