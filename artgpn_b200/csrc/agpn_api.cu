@@ -16,6 +16,7 @@
 #include "agpn_eval.cuh"
 #include "agpn_predict.cuh"
 #include "agpn_small.cuh"
+#include "agpn_tma.cuh"
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
@@ -83,12 +84,17 @@ struct agpn_ctx {
     std::vector<Ev> evs;
     bool attrs_set = false;
     size_t small_smem_set = 0;
-    int group = 4;             // block columns per wide trailing update (AGPN_GROUP)
+    // TMA descriptors of the batch workspace d_A (box 128 x 16 and 64 x 16 doubles, 128-byte swizzle)
+    bool use_tma = false;      // AGPN_SYRK=tma | tma_nomc selects the TMA trailing-update kernel (default: cp.async, faster by 1-4 %)
+    bool maps_valid = false;
+    int tma_mc = 1;            // multicast the shared A operand inside the CTA pair (AGPN_SYRK=tma_nomc: off)
+    CUtensorMap tmA, tmB;
+    int group = 8;             // block columns per wide trailing update (AGPN_GROUP)
     bool no_fast_asm = false;  // AGPN_GENERIC_ASM=1 forces the generic assembly kernel
     bool no_small = false;     // AGPN_NO_SMALL=1 disables the fused small-N kernel
     // sub-batch streams: the matrices of a batch are split over nsub streams so that one sub-batch's
     // small serial kernels (diagonal block, panel solve) overlap another's wide tensor update
-    int nsub = 3;              // AGPN_STREAMS
+    int nsub = 6;              // AGPN_STREAMS
     cudaStream_t sub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -106,12 +112,43 @@ extern "C" int agpn_kernel_npars(int family, int kind) { return kernel_npars(fam
 extern "C" int agpn_mean_npars(int kind) { return mean_npars(kind); }
 extern "C" long long agpn_launch_count(void) { return g_launches.load(); }
 
+// ---- TMA tensor maps (driver entry point fetched through the runtime; libcuda is not linked) ----
+typedef CUresult (*agpn_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static agpn_encode_tiled_fn get_encode_tiled() {
+    static agpn_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (agpn_encode_tiled_fn)p;
+    }
+    return fn;
+}
+
+// maps over matrices [nmat][n_pad][ld] (row-major doubles): boxes of box_rows x 16 elements
+static bool make_batch_map(CUtensorMap* out, double* base, size_t nmat, int n_pad, int ld, int box_rows) {
+    agpn_encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)ld, (cuuint64_t)n_pad, (cuuint64_t)nmat};
+    const cuuint64_t gstride[2] = {(cuuint64_t)ld * 8, (cuuint64_t)n_pad * ld * 8};
+    const cuuint32_t box[3] = {GEMM_KC, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int set_kernel_attrs(agpn_ctx* c) {
     if (c->attrs_set) return 0;
     CUDA_TRY(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
     c->attrs_set = true;
     return 0;
 }
@@ -134,9 +171,10 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     c->npad = c->nblk * TB;
     c->tmean = host_mean(time, N);
     c->t0 = time[0];
-    if (const char* e = getenv("AGPN_GROUP")) c->group = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char* e = getenv("AGPN_GROUP")) c->group = atoi(e) > 0 ? atoi(e) : 8;
     if (const char* e = getenv("AGPN_GENERIC_ASM")) c->no_fast_asm = atoi(e) != 0;
     if (const char* e = getenv("AGPN_NO_SMALL")) c->no_small = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_SYRK")) { c->use_tma = strncmp(e, "tma", 3) == 0; c->tma_mc = strcmp(e, "tma_nomc") != 0; }
     memset(&c->S, 0, sizeof(Structure));
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_t, sizeof(double) * N)) != cudaSuccess ||
@@ -298,6 +336,8 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         c->cap_mats = 0;
         const size_t np = (size_t)c->npad;
         CUDA_TRY(cudaMalloc(&c->d_A, sizeof(double) * nmat * np * np));
+        c->maps_valid = c->use_tma && make_batch_map(&c->tmA, c->d_A, nmat, c->npad, c->npad, TB) &&
+                        make_batch_map(&c->tmB, c->d_A, nmat, c->npad, c->npad, BN);
         CUDA_TRY(cudaMalloc(&c->d_Linv, sizeof(double) * nmat * TB * TB));
         CUDA_TRY(cudaMalloc(&c->d_rhs, sizeof(double) * nmat * np));
         CUDA_TRY(cudaMalloc(&c->d_logdet, sizeof(double) * nmat));
@@ -334,7 +374,10 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
         for (int k = k0; k < kend; ++k) {
             if (k > k0) {
                 PhaseScope ps(c, st, PH_SYRK, cur);
-                syrk_kernel<<<dim3(2 * (g.nblk - k), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
+                if (c->maps_valid)
+                    syrk_tma_kernel<<<dim3(2 * (g.nblk - k), g.nmat), TMA_THREADS, TMA_SMEM_BYTES, st>>>(c->tmA, c->tmB, g, k0, k - k0, k, 1, c->tma_mc);
+                else
+                    syrk_kernel<<<dim3(2 * (g.nblk - k), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
                 LAUNCH_CHECK();
             }
             {
@@ -351,7 +394,10 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
         const int nt = g.nblk - kend;
         if (nt > 0) {
             PhaseScope ps(c, st, PH_SYRK, cur);
-            syrk_kernel<<<dim3(nt * (nt + 1), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
+            if (c->maps_valid)
+                syrk_tma_kernel<<<dim3(nt * (nt + 1), g.nmat), TMA_THREADS, TMA_SMEM_BYTES, st>>>(c->tmA, c->tmB, g, k0, kend - k0, kend, 0, c->tma_mc);
+            else
+                syrk_kernel<<<dim3(nt * (nt + 1), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
             LAUNCH_CHECK();
         }
     }
@@ -500,6 +546,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
         g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = nmat;
         g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
         g.info = d_infoflag;
+        g.A0 = c->d_A; g.mat0 = 0;
         const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
         if (nsub == 1) {
             if (run_cholesky(c, g, st, &cur)) return 1;
@@ -517,6 +564,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
                 gs.quad = g.quad + m0;
                 gs.info = g.info + m0;
                 gs.nmat = m1 - m0;
+                gs.mat0 = m0;
                 CUDA_TRY(cudaStreamWaitEvent(c->sub[si], c->ev_fork, 0));
                 if (run_cholesky(c, gs, c->sub[si], nullptr)) return 1;
                 CUDA_TRY(cudaEventRecord(c->ev_join[si], c->sub[si]));
@@ -690,6 +738,7 @@ extern "C" int agpn_predict(agpn_ctx* c, const double* theta, int series, int M,
     g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = 1;
     g.Linv = c->d_LinvAll; g.linv_blocks = c->nblk; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
     g.info = c->d_info;
+    g.A0 = c->d_A; g.mat0 = 0;
     if (run_cholesky(c, g, st, nullptr)) return 1;
     kss_kernel<<<(M + 127) / 128, 128, 0, st>>>(c->S, c->d_theta, series, d_ts, M, d_kss);
     LAUNCH_CHECK();
@@ -753,7 +802,7 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     cudaStream_t st = (cudaStream_t)stream;
     agpn_ctx tmp;
     tmp.device = device;
-    if (const char* e = getenv("AGPN_GROUP")) tmp.group = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char* e = getenv("AGPN_GROUP")) tmp.group = atoi(e) > 0 ? atoi(e) : 8;
     if (set_kernel_attrs(&tmp)) return 1;
     double* d_linv = nullptr;
     CUDA_TRY(cudaMalloc(&d_linv, sizeof(double) * (size_t)nmat * TB * TB));
@@ -763,6 +812,9 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     CholArgs g;
     g.A = A; g.mat_stride = (long long)n_pad * n_pad; g.ld = n_pad; g.nblk = n_pad / TB; g.nmat = nmat; g.Linv = d_linv;
     g.linv_blocks = 1; g.rhs = rhs; g.logdet = logdet; g.quad = quad; g.info = info;
+    g.A0 = A; g.mat0 = 0;
+    if (const char* e = getenv("AGPN_SYRK")) { tmp.use_tma = strncmp(e, "tma", 3) == 0; tmp.tma_mc = strcmp(e, "tma_nomc") != 0; }
+    tmp.maps_valid = tmp.use_tma && make_batch_map(&tmp.tmA, A, nmat, n_pad, n_pad, TB) && make_batch_map(&tmp.tmB, A, nmat, n_pad, n_pad, BN);
     int rc = run_cholesky(&tmp, g, st, nullptr);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(d_linv);

@@ -49,6 +49,8 @@ struct CholArgs {
     double* logdet;         // [nmat]  accumulated
     double* quad;           // [nmat]  accumulated |z|^2
     int* info;              // [nmat]  0 ok / 1 not positive definite
+    double* A0;             // base of the whole batch allocation the tensor maps describe (TMA path)
+    int mat0;               // index of this launch's first matrix inside that allocation
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {

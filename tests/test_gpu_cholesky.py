@@ -28,8 +28,16 @@ def _spd(rng, nmat, n, cond_jitter):
     return X @ X.transpose(0, 2, 1) + cond_jitter * np.eye(n)
 
 
-@pytest.mark.parametrize("n,nmat", [(128, 5), (256, 3), (640, 2)])
-def test_potrf_batched_vs_numpy(n, nmat):
+@pytest.fixture(params=["cpasync", "tma", "tma_nomc"])
+def syrk_variant(request, monkeypatch):
+    """Trailing-update kernel: cp.async + mbarrier pipeline (default) or the TMA (cp.async.bulk.tensor)
+    producer-warp kernel with / without cluster multicast (AGPN_SYRK, read per call here)."""
+    monkeypatch.setenv("AGPN_SYRK", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("n,nmat", [(128, 5), (256, 3), (640, 2), (1408, 2)])
+def test_potrf_batched_vs_numpy(n, nmat, syrk_variant):
     rng = np.random.default_rng(n)
     K = _spd(rng, nmat, n, 1e-2 * n)
     r = rng.normal(size=(nmat, n))
