@@ -313,6 +313,15 @@ def main():
         syrk_tf = W_local * p * syrk_tiles * 2.0 * 128 ** 3 / (phase[4] * 1e-3) / 1e12 if phase[4] > 0 else None
         asm_bytes = W_local * 4.0 * p * N * (N + 1)               # triangle-only store: B_tri = 4 p N (N+1)
         asm_gbs = asm_bytes / (phase[1] * 1e-3) / 1e9
+        chol_traffic = asm_traffic = None                         # DRAM bytes from the committed ncu pass
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f)
+            if tr.get("workload") == args.workload and args.weights == "Constant":
+                chol_traffic = tr["cholesky_dram_bytes_per_step"] * W_local / tr["walkers"]
+                asm_traffic = tr["assembly_dram_bytes_per_launch"] * W_local / tr["walkers"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -332,12 +341,13 @@ def main():
                          "frac": chol_tf / float(peak_tf[0]),
                          "peak_source": "DMMA.8x8x4 issue peak measured in this run (agpn_dmma_peak); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
-                         "flops_per_launch_group": chol_flops, "ms": chol_ms, "traffic": None,
+                         "flops_per_launch_group": chol_flops, "ms": chol_ms, "traffic": chol_traffic,
+                         "traffic_note": "DRAM bytes of all Cholesky launches of one step, ncu pass in profiles/ (scaled by walkers)",
                          "syrk_only_tflops": syrk_tf},
-            "roofline_assembly": {"bound": "hbm", "kernel": "assemble_kernel (lower block triangle only)",
+            "roofline_assembly": {"bound": "hbm", "kernel": "assemble_fast_kernel (lower block triangle only; generic assemble_kernel for other kernel classes)",
                                   "achieved": asm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                   "frac": asm_gbs / peaks.get("hbm_gbs"), "peak_source": peak_src,
-                                  "bytes_per_launch": asm_bytes, "ms": float(phase[1]), "traffic": None},
+                                  "bytes_per_launch": asm_bytes, "ms": float(phase[1]), "traffic": asm_traffic},
             "phase_ms": {"mean_residual": float(phase[0]), "assembly": float(phase[1]), "potrf_diag": float(phase[2]),
                          "trsm": float(phase[3]), "syrk": float(phase[4]), "finalize": float(phase[5]),
                          "launches": [int(x) for x in nl]},
