@@ -83,7 +83,6 @@ struct agpn_ctx {
     struct Ev { cudaEvent_t a, b; int ph; };
     std::vector<Ev> evs;
     bool attrs_set = false;
-    size_t small_smem_set = 0;
     // TMA descriptors of the batch workspace d_A (box 128 x 16 and 64 x 16 doubles, 128-byte swizzle)
     bool use_tma = false;      // AGPN_SYRK=tma | tma_nomc selects the TMA trailing-update kernel (default: cp.async, faster by 1-4 %)
     bool maps_valid = false;
@@ -149,6 +148,13 @@ static int set_kernel_attrs(agpn_ctx* c) {
     CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+    // function attributes are per function (not per context): always allow the largest K0 configuration
+    {
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, small_fused_kernel));
+        CUDA_TRY(cudaFuncSetAttribute(small_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      232448 - (int)fa.sharedSizeBytes));
+    }
     c->attrs_set = true;
     return 0;
 }
@@ -524,11 +530,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
             sa.theta = d_theta; sa.t = c->d_t; sa.yerr = c->d_yerr; sa.rhs = c->d_rhs; sa.rhs_stride = c->npad;
             sa.N = c->N; sa.nb = small_nb; sa.fast = fast ? 1 : 0; sa.torigin = c->t0;
             sa.logdet = c->d_logdet; sa.quad = c->d_quad; sa.info = d_infoflag; sa.kflag = d_kflag;
-            const size_t smem = small_smem_bytes(small_nb, c->q);
-            if (smem > c->small_smem_set) {
-                CUDA_TRY(cudaFuncSetAttribute(small_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                c->small_smem_set = smem;
-            }
+            const size_t smem = small_smem_bytes(small_nb, c->q);    // <= 227 KB for nb <= 12, q <= 8 (attribute set at create)
             small_fused_kernel<<<dim3(p, Ww), 256, smem, st>>>(c->S, sa);
             LAUNCH_CHECK();
         } else {
