@@ -89,6 +89,8 @@ struct agpn_ctx {
     int tma_mc = 1;            // multicast the shared A operand inside the CTA pair (AGPN_SYRK=tma_nomc: off)
     CUtensorMap tmA, tmB;
     int group = 8;             // block columns per wide trailing update (AGPN_GROUP)
+    bool group_fixed = false;  // AGPN_GROUP given: no adaptation to the batch size
+    int group_eff = 8;         // group used by the current call (set from the TOTAL number of matrices)
     bool no_fast_asm = false;  // AGPN_GENERIC_ASM=1 forces the generic assembly kernel
     bool no_small = false;     // AGPN_NO_SMALL=1 disables the fused small-N kernel
     // sub-batch streams: the matrices of a batch are split over nsub streams so that one sub-batch's
@@ -177,7 +179,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     c->npad = c->nblk * TB;
     c->tmean = host_mean(time, N);
     c->t0 = time[0];
-    if (const char* e = getenv("AGPN_GROUP")) c->group = atoi(e) > 0 ? atoi(e) : 8;
+    if (const char* e = getenv("AGPN_GROUP")) { c->group = atoi(e) > 0 ? atoi(e) : 8; c->group_fixed = true; }
     if (const char* e = getenv("AGPN_GENERIC_ASM")) c->no_fast_asm = atoi(e) != 0;
     if (const char* e = getenv("AGPN_NO_SMALL")) c->no_small = atoi(e) != 0;
     if (const char* e = getenv("AGPN_SYRK")) { c->use_tma = strncmp(e, "tma", 3) == 0; c->tma_mc = strcmp(e, "tma_nomc") != 0; }
@@ -374,7 +376,9 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
 static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor) {
     size_t local_cursor = 0;
     size_t& cur = cursor ? *cursor : local_cursor;
-    const int group = c->group < 1 ? 1 : c->group;
+    // few matrices: the left-looking narrow updates of a deep group have too few CTAs to fill the GPU
+    // (measured: 12 matrices of 2048^2 -> group 2 is 7 % faster than 8; >= 48 matrices -> 8 is best)
+    const int group = c->group_eff < 1 ? 1 : c->group_eff;
     for (int k0 = 0; k0 < g.nblk; k0 += group) {
         const int kend = (k0 + group < g.nblk) ? k0 + group : g.nblk;
         for (int k = k0; k < kend; ++k) {
@@ -549,6 +553,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
         g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
         g.info = d_infoflag;
         g.A0 = c->d_A; g.mat0 = 0;
+        c->group_eff = (c->group_fixed || nmat >= 24) ? c->group : 2;
         const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
         if (nsub == 1) {
             if (run_cholesky(c, g, st, &cur)) return 1;
@@ -741,6 +746,7 @@ extern "C" int agpn_predict(agpn_ctx* c, const double* theta, int series, int M,
     g.Linv = c->d_LinvAll; g.linv_blocks = c->nblk; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
     g.info = c->d_info;
     g.A0 = c->d_A; g.mat0 = 0;
+    c->group_eff = c->group_fixed ? c->group : 2;
     if (run_cholesky(c, g, st, nullptr)) return 1;
     kss_kernel<<<(M + 127) / 128, 128, 0, st>>>(c->S, c->d_theta, series, d_ts, M, d_kss);
     LAUNCH_CHECK();
@@ -804,7 +810,7 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     cudaStream_t st = (cudaStream_t)stream;
     agpn_ctx tmp;
     tmp.device = device;
-    if (const char* e = getenv("AGPN_GROUP")) tmp.group = atoi(e) > 0 ? atoi(e) : 8;
+    if (const char* e = getenv("AGPN_GROUP")) { tmp.group = atoi(e) > 0 ? atoi(e) : 8; tmp.group_fixed = true; }
     if (set_kernel_attrs(&tmp)) return 1;
     double* d_linv = nullptr;
     CUDA_TRY(cudaMalloc(&d_linv, sizeof(double) * (size_t)nmat * TB * TB));
@@ -817,6 +823,7 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     g.A0 = A; g.mat0 = 0;
     if (const char* e = getenv("AGPN_SYRK")) { tmp.use_tma = strncmp(e, "tma", 3) == 0; tmp.tma_mc = strcmp(e, "tma_nomc") != 0; }
     tmp.maps_valid = tmp.use_tma && make_batch_map(&tmp.tmA, A, nmat, n_pad, n_pad, TB) && make_batch_map(&tmp.tmB, A, nmat, n_pad, n_pad, BN);
+    tmp.group_eff = (tmp.group_fixed || nmat >= 24) ? tmp.group : 2;
     int rc = run_cholesky(&tmp, g, st, nullptr);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(d_linv);

@@ -501,7 +501,11 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
     // ---- factor: panels of 16 columns; the diagonal block of panel pb+1 (serial, one warp) is
     //      factorised while the other warps apply panel pb to the rest of the trailing matrix --------
     if (warp == 0) potrf16_warp(S, invd, scr, 0, lane, &s_fail);
+#ifdef WHATIF_SKIP_FACTOR
+    for (int pb = 8; pb < 8; ++pb) {
+#else
     for (int pb = 0; pb < 8; ++pb) {
+#endif
         const int c0 = pb * 16;
         __syncthreads();
         // B: rows below the diagonal block, one thread per row: x L_D^T = b
@@ -573,7 +577,11 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
     {
         const int j = warp;
         double* sc = scr + warp * 16 * PD_DV_LD;
+#ifdef WHATIF_SKIP_INV2
+        for (int i = 8; i < 8; ++i) {
+#else
         for (int i = j + 1; i < 8; ++i) {
+#endif
             double acc[4][2][2][2];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
