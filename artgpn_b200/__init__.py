@@ -9,9 +9,10 @@ from . import weight
 from . import node
 from . import mean
 from . import arttwo
+from . import art
 from .arttwo import network
 from ._kernelbase import set_device, get_device
 from ._lib import AgpnError, LIB_PATH
 
-__all__ = ["weight", "node", "mean", "arttwo", "network", "set_device", "get_device", "AgpnError", "LIB_PATH"]
+__all__ = ["weight", "node", "mean", "arttwo", "art", "network", "set_device", "get_device", "AgpnError", "LIB_PATH"]
 __version__ = "0.1.0"

@@ -372,6 +372,35 @@ class network(object):
             raise ValueError("array must not contain infs or NaNs")
         return mu, sd, time
 
+    def prediction_cov(self, nodes=None, weights=None, means=None, jitters=None, time=None, dataset=1,
+                       train_jitter=None):
+        """
+        Predictive mean, standard deviation AND the full covariance matrix (the `y_cov` the reference
+        builds at arttwo.py:393 but does not return; legacy art.network.prediction returns it, art.py:354).
+
+        Computed on the GPU as the Schur complement of a partial blocked Cholesky of [K . ; K* K**].
+        Dense (N + M)^2 workspace -- meant for grids of up to a few 10^4 points.
+        train_jitter: jitter used in the training block only (legacy art.network quirk); default: the
+        dataset's entry of `jitters`.  Returns (y_mean, y_std, y_cov).
+        """
+        time = np.asarray(time, dtype=np.float64)
+        time = time if time.any() else np.asarray(self.time, dtype=np.float64)
+        s = Structure(self.p, self.q, nodes, weights, means)
+        self._apply_structure(s)
+        theta = s.pack(nodes, weights, means, jitters)
+        ts = np.ascontiguousarray(time, dtype=np.float64)
+        mu = np.empty(ts.size)
+        cov = np.empty((ts.size, ts.size))
+        status = np.zeros(1, dtype=np.int32)
+        tj = float("nan") if train_jitter is None else float(train_jitter)
+        _lib.check(_lib.load().agpn_predict_cov(self._ctx(), _lib.ptr(theta), dataset - 1, ts.size, _lib.ptr(ts), tj,
+                                                _lib.ptr(mu), _lib.ptr(cov), _lib.ptr(status), None))
+        if status[0] == STATUS_NOT_PD:
+            raise np.linalg.LinAlgError("matrix is not positive definite")
+        if status[0] == STATUS_NOT_FINITE:
+            raise ValueError("array must not contain infs or NaNs")
+        return mu, np.sqrt(np.diag(cov)), cov
+
     # ---- profiling hooks used by bench.py -----------------------------------------------------
     def set_profiling(self, enable):
         _lib.check(_lib.load().agpn_set_profiling(self._ctx(), 1 if enable else 0))

@@ -76,6 +76,10 @@ struct agpn_ctx {
     double* d_V = nullptr;
     size_t cap_M = 0;
     double* d_pred = nullptr;  // tstar | mstar | kss | mean | std, 5 * cap_M
+    size_t cap_aug = 0;        // augmented [K . ; K* K**] matrix of agpn_predict_cov, doubles
+    double* d_aug = nullptr;
+    size_t cap_augv = 0;
+    double* d_augv = nullptr;  // rhs of the augmented system | second theta row
     // profiling
     bool profiling = false;
     double phase_ms[PH_COUNT] = {0, 0, 0, 0, 0, 0};
@@ -230,7 +234,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_t); cudaFree(c->d_y); cudaFree(c->d_yerr);
     cudaFree(c->d_A); cudaFree(c->d_Linv); cudaFree(c->d_rhs); cudaFree(c->d_logdet); cudaFree(c->d_quad);
     cudaFree(c->d_info); cudaFree(c->d_theta); cudaFree(c->d_out); cudaFree(c->d_status);
-    cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred);
+    cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
     delete c;
     return 0;
 }
@@ -373,14 +377,17 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
 // the (narrow) update from the group's earlier columns, then its diagonal block is factorised and
 // its panel solved; after the group the whole trailing matrix takes ONE update of depth
 // 128 * group (wide).  group = 1 is the plain right-looking algorithm.
-static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor) {
+static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor, int kstop = -1) {
     size_t local_cursor = 0;
     size_t& cur = cursor ? *cursor : local_cursor;
     // few matrices: the left-looking narrow updates of a deep group have too few CTAs to fill the GPU
     // (measured: 12 matrices of 2048^2 -> group 2 is 7 % faster than 8; >= 48 matrices -> 8 is best)
     const int group = c->group_eff < 1 ? 1 : c->group_eff;
-    for (int k0 = 0; k0 < g.nblk; k0 += group) {
-        const int kend = (k0 + group < g.nblk) ? k0 + group : g.nblk;
+    // kstop < nblk: partial factorisation -- only the first kstop block columns are eliminated; the
+    // remaining trailing block then holds the Schur complement (used for the predictive covariance)
+    if (kstop < 0 || kstop > g.nblk) kstop = g.nblk;
+    for (int k0 = 0; k0 < kstop; k0 += group) {
+        const int kend = (k0 + group < kstop) ? k0 + group : kstop;
         for (int k = k0; k < kend; ++k) {
             if (k > k0) {
                 PhaseScope ps(c, st, PH_SYRK, cur);
@@ -763,6 +770,123 @@ extern "C" int agpn_predict(agpn_ctx* c, const double* theta, int series, int M,
     CUDA_TRY(cudaMemcpyAsync(&h_flags[1], d_kflag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&h_flags[2], d_rflag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (status) *status = h_flags[1] ? AGPN_STATUS_NOT_FINITE : (h_flags[0] ? AGPN_STATUS_NOT_PD : (h_flags[2] ? AGPN_STATUS_NOT_FINITE : AGPN_STATUS_OK));
+    return 0;
+}
+
+// mean[m] = mstar[m] - rhs_aug[Npad + m] ; cov = symmetrised trailing block of the augmented matrix
+__global__ void extract_cov_kernel(const double* aug, int T, int npad, int M, const double* rhs_aug, const double* mstar,
+                                   double* mean_out, double* cov_out) {
+    const size_t n = (size_t)M * M;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / M), j = (int)(idx % M);
+        const int r = i >= j ? i : j, cc = i >= j ? j : i;
+        cov_out[idx] = aug[(size_t)(npad + r) * T + npad + cc];
+        if (j == 0) mean_out[i] = mstar[i] - rhs_aug[npad + i];
+    }
+}
+
+extern "C" int agpn_predict_cov(agpn_ctx* c, const double* theta, int series, int M, const double* tstar,
+                                double train_jitter, double* mean_out, double* cov_out, int* status, void* stream) {
+    if (!c || !theta || !tstar || !mean_out || !cov_out) USAGE_FAIL("agpn_predict_cov: null pointer");
+    if (!c->has_structure) USAGE_FAIL("agpn_predict_cov: call agpn_set_structure first");
+    if (series < 0 || series >= c->p) USAGE_FAIL("agpn_predict_cov: series out of range");
+    if (M < 1) USAGE_FAIL("agpn_predict_cov: empty prediction grid");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = c->S.D;
+    const size_t npad = (size_t)c->npad;
+    const size_t Mpad = ((size_t)M + TB - 1) / TB * TB;
+    const size_t T = npad + Mpad;
+    if (T > 46000) USAGE_FAIL("agpn_predict_cov: N + M too large for a dense covariance (use agpn_predict)");
+    if (ensure_batch_workspace(c, 1, 1)) return 1;
+    if (T * T > c->cap_aug) {
+        cudaFree(c->d_aug);
+        c->d_aug = nullptr;
+        c->cap_aug = 0;
+        CUDA_TRY(cudaMalloc(&c->d_aug, sizeof(double) * T * T));
+        c->cap_aug = T * T;
+    }
+    if (T + 2 * (size_t)D > c->cap_augv) {
+        cudaFree(c->d_augv);
+        c->d_augv = nullptr;
+        c->cap_augv = 0;
+        CUDA_TRY(cudaMalloc(&c->d_augv, sizeof(double) * (T + 2 * (size_t)D)));
+        c->cap_augv = T + 2 * (size_t)D;
+    }
+    if ((size_t)M > c->cap_M) {
+        cudaFree(c->d_pred);
+        c->d_pred = nullptr;
+        c->cap_M = 0;
+        CUDA_TRY(cudaMalloc(&c->d_pred, sizeof(double) * 5 * (size_t)M));
+        c->cap_M = M;
+    }
+    double* d_rhs = c->d_augv;                 // [T]
+    double* d_th = c->d_augv + T;              // theta (prediction blocks) | theta with the training jitter
+    double* d_ts = c->d_pred;
+    double* d_ms = c->d_pred + c->cap_M;
+    double* d_mu = c->d_pred + 3 * c->cap_M;
+    std::vector<double> th2(theta, theta + D);
+    if (train_jitter == train_jitter) th2[c->S.jit_off + series] = train_jitter;    // not NaN: legacy art.network quirk
+    CUDA_TRY(cudaMemcpyAsync(d_th, theta, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_th + D, th2.data(), sizeof(double) * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ts, tstar, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));       // th2 is a local
+    CUDA_TRY(cudaMemsetAsync(d_rhs, 0, sizeof(double) * T, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 3 * c->cap_mats, st));
+    int* d_kflag = c->d_info + c->cap_mats;
+    int* d_rflag = c->d_info + 2 * c->cap_mats;
+    MeanArgs m;
+    m.theta = d_th; m.t = c->d_t; m.n = c->N; m.n_pad = c->npad; m.tmean = c->tmean; m.t0 = c->t0; m.y = c->d_y;
+    m.out = d_rhs; m.series0 = series; m.nser = 1; m.subtract = 1; m.rflag = d_rflag;
+    mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
+    LAUNCH_CHECK();
+    m.t = d_ts; m.n = M; m.n_pad = M; m.tmean = host_mean(tstar, M); m.t0 = tstar[0]; m.y = nullptr; m.out = d_ms;
+    m.subtract = 0; m.rflag = nullptr;
+    mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
+    LAUNCH_CHECK();
+    // augmented matrix [K + sigma^2 + s^2 , . ; K* , K** + s^2] (arttwo.py:367-387), lower block triangle
+    AsmArgs a;
+    a.theta = d_th + D; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
+    a.yerr = c->d_yerr; a.out = c->d_aug; a.mat_stride = (long long)(T * T); a.ld = (int)T; a.series0 = series; a.nser = 1;
+    a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1; a.use_trig = 1; a.vec2 = 1;
+    a.torigin = c->t0; a.kflag = d_kflag;
+    if (launch_assemble(c, a, 1, st)) return 1;
+    a.theta = d_th; a.ta = d_ts; a.tb = c->d_t; a.na = M; a.nb = c->N; a.rows_out = (int)Mpad; a.cols_out = c->npad;
+    a.out = c->d_aug + npad * T; a.lower_only = 0; a.square = (M == c->N) ? 1 : 0; a.add_err = 0; a.add_jit = 0;
+    a.pad_identity = 0; a.use_trig = 0; a.kflag = nullptr;
+    if (launch_assemble(c, a, 1, st)) return 1;
+    a.ta = d_ts; a.tb = d_ts; a.na = M; a.nb = M; a.rows_out = (int)Mpad; a.cols_out = (int)Mpad;
+    a.out = c->d_aug + npad * T + npad; a.lower_only = 1; a.square = 1; a.add_err = 0; a.add_jit = 1; a.pad_identity = 1;
+    if (launch_assemble(c, a, 1, st)) return 1;
+    // eliminate the training block columns only: the trailing block becomes K** + s^2 - K* K^-1 K*^T and
+    // the trailing part of the right-hand side becomes -K* K^-1 r
+    CholArgs g;
+    g.A = c->d_aug; g.mat_stride = (long long)(T * T); g.ld = (int)T; g.nblk = (int)(T / TB); g.nmat = 1;
+    g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad; g.info = c->d_info;
+    g.A0 = c->d_aug; g.mat0 = 0;
+    const bool maps_were = c->maps_valid;
+    c->maps_valid = false;                      // the tensor maps describe the batch workspace, not this matrix
+    c->group_eff = c->group_fixed ? c->group : 2;
+    const int rc = run_cholesky(c, g, st, nullptr, c->nblk);
+    c->maps_valid = maps_were;
+    if (rc) return 1;
+    double* d_cov = nullptr;
+    CUDA_TRY(cudaMalloc(&d_cov, sizeof(double) * (size_t)M * M));
+    extract_cov_kernel<<<1024, 256, 0, st>>>(c->d_aug, (int)T, c->npad, M, d_rhs, d_ms, d_mu, d_cov);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mean_out, d_mu, sizeof(double) * M, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cov_out, d_cov, sizeof(double) * (size_t)M * M, cudaMemcpyDeviceToHost, st);
+    int h_flags[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flags[0], c->d_info, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flags[1], d_kflag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flags[2], d_rflag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_cov);
+    CUDA_TRY(e);
     if (status) *status = h_flags[1] ? AGPN_STATUS_NOT_FINITE : (h_flags[0] ? AGPN_STATUS_NOT_PD : (h_flags[2] ? AGPN_STATUS_NOT_FINITE : AGPN_STATUS_OK));
     return 0;
 }

@@ -115,6 +115,18 @@ int agpn_predict(agpn_ctx* ctx, const double* theta, int series, int M, const do
                  double* mean_out, double* std_out, int* status, void* stream);
 
 /*
+ * Predictive mean AND full covariance (what y_cov of arttwo.py:393 / the legacy art.py:350-354 hold):
+ * cov_out[M][M] = K** + s^2 I - K* K^-1 K*^T, mean_out[M] as agpn_predict.  Computed as the Schur
+ * complement of a partial blocked Cholesky of the augmented matrix [K . ; K* K**] with the same
+ * kernels as the likelihood.  train_jitter: NaN = the theta row's jitter is used for the training block
+ * too; a number reproduces the legacy art.network quirk (art.py:320 uses the constructor's jitter for
+ * the training block and the call's jitter for K**).  Dense (N + M)^2 workspace: meant for M up to a
+ * few 10^4.  All pointers host.
+ */
+int agpn_predict_cov(agpn_ctx* ctx, const double* theta, int series, int M, const double* tstar,
+                     double train_jitter, double* mean_out, double* cov_out, int* status, void* stream);
+
+/*
  * Replaces one kernel object's __call__ (node.py / weight.py): element-wise value on a
  * [rows][cols] lag array r, or on t1[rows] x t2[cols] for Linear / Polynomial (r ignored).
  * Host pointers; runs on `device`.  square_quirk as above (1 iff rows == cols in the reference).

@@ -21,6 +21,7 @@ from scipy.linalg import cho_factor, cho_solve, solve_triangular, LinAlgError
 __all__ = [
     "spec", "node_matrix", "weight_matrix", "node_eval", "weight_eval", "mean_eval", "mean_vector",
     "covariance_block", "compute_matrix", "log_likelihood", "prediction", "prediction_reference_form",
+    "art_weights", "art_log_likelihood", "art_prediction",
 ]
 
 _NONSTATIONARY = ("Linear", "Polynomial")          # arttwo.py:58,66 isinstance test
@@ -288,9 +289,11 @@ def prediction(time, y, yerr, q, nodes, weights, means, jitters, tstar, dataset=
     return mu, np.sqrt(var)
 
 
-def prediction_reference_form(time, y, yerr, q, nodes, weights, means, jitters, tstar, dataset=1):
+def prediction_reference_form(time, y, yerr, q, nodes, weights, means, jitters, tstar, dataset=1,
+                              train_jitter=None, return_cov=False):
     """arttwo.py:367-395 as written (M x M intermediates); small M only.  Used to show that the
-    diagonal-only form above is the same function."""
+    diagonal-only form above is the same function.  train_jitter / return_cov cover the legacy
+    art.network.prediction (art.py:318-354: constructor jitter in the training block, full y_cov)."""
     time = np.asarray(time, float)
     tstar = np.asarray(tstar, float)
     y = np.asarray(y, float)
@@ -299,11 +302,35 @@ def prediction_reference_form(time, y, yerr, q, nodes, weights, means, jitters, 
     d = dataset - 1
     resid = y - mean_vector(means, time, p) if means else y
     K = covariance_block(time, nodes, weights, d, q)
-    K[np.diag_indices(N)] += yerr[d] ** 2 + jitters[d] ** 2
+    K[np.diag_indices(N)] += yerr[d] ** 2 + (jitters[d] if train_jitter is None else train_jitter) ** 2
     U = cho_factor(K)
     sol = cho_solve(U, resid[d])
     Ks = covariance_block(time, nodes, weights, d, q, ta=tstar, tb=time)
     Kss = covariance_block(time, nodes, weights, d, q, ta=tstar) + jitters[d] ** 2 * np.identity(tstar.size)
     mu = Ks @ sol + (mean_vector(means, tstar, p)[d] if means else 0.0)
     quad = np.array([Ks @ cho_solve(U, Ks[i, :]) for i in range(tstar.size)])
+    if return_cov:
+        return mu, np.sqrt(np.diag(Kss - quad)), Kss - quad
     return mu, np.sqrt(np.diag(Kss - quad))
+
+
+def art_weights(q, p, weight_spec, weights_values):
+    """Legacy art.network: one weight class, amplitude per (series, node) from weights_values
+    (art.py:253-261).  weight_spec = (name, pars) of weights[0]."""
+    name, pars = spec(weight_spec)
+    return [(name, [float(weights_values[j + q * i])] + list(pars[1:])) for i in range(p) for j in range(q)]
+
+
+def art_log_likelihood(time, y, yerr, q, nodes, weight_spec, weights_values, means, jitters):
+    """art.py:228-276: the constructor squared yerr (art.py:58) and the likelihood squares it again."""
+    y = np.asarray(y, float)
+    return log_likelihood(time, y, np.asarray(yerr, float) ** 2, q, nodes,
+                          art_weights(q, y.shape[0], weight_spec, weights_values), means, jitters)
+
+
+def art_prediction(time, y, yerr, q, nodes, weight_spec, weights_values, means, jitters, ctor_jitters, tstar, dataset=1):
+    """art.py:280-354 -> (mean, std, cov)."""
+    y = np.asarray(y, float)
+    return prediction_reference_form(time, y, np.asarray(yerr, float) ** 2, q, nodes,
+                                     art_weights(q, y.shape[0], weight_spec, weights_values), means, jitters, tstar,
+                                     dataset, train_jitter=ctor_jitters[dataset - 1], return_cov=True)

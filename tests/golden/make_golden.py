@@ -28,6 +28,7 @@ sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
 
 from artgpn.arttwo import network as ref_network          # noqa: E402
+from artgpn.art import network as ref_art_network         # noqa: E402
 from artgpn import node as ref_node, weight as ref_weight, mean as ref_mean   # noqa: E402
 import scipy                                                # noqa: E402
 from artgpn_b200 import synth                               # noqa: E402  (pure-numpy generators)
@@ -68,7 +69,7 @@ def main():
     data = {}
     arrays = {}
     cases = {"versions": {"numpy": np.__version__, "scipy": scipy.__version__}, "loglike": [], "predict": [],
-             "kernels": [], "means": [], "covariance": [], "batch": []}
+             "kernels": [], "means": [], "covariance": [], "batch": [], "legacy_art": []}
 
     # ---- example data -------------------------------------------------------------------------
     corot = np.loadtxt(os.path.join(REF, "examples/CoRoT-7/corot7_data.rdb"), skiprows=1)
@@ -290,6 +291,36 @@ def main():
         arrays[key + "_meanvec"] = net._mean(means)
         arrays[key + "_meanvec_grid33"] = net._mean(means, tgrid)
         cases["covariance"].append({"case": case["name"], "key": key})
+
+    # ---- legacy art.network (art.py): shared weight class + weights_values, sigma^4 quirk, (mean, std, cov)
+    for name, dname, nspecs, wspec, wvals, ctor_jit, call_jit, mspecs in (
+            ("art_sun50_se", "sun50", [["QuasiPeriodic", [15.0, 25.0, 0.8]]], ["SquaredExponential", [1.0, 30.0]],
+             [1.0, 2.0, 0.5], [0.9, 0.5, 1.2], [0.7, 0.6, 1.0],
+             [["Linear", [0.0, -16.9]], ["Linear", [0.0, -88.0]], ["Linear", [0.0, 7784.0]]]),
+            ("art_corot20_const_q2", "corot20x3", [["Periodic", [21.0, 0.6]], ["Matern32", [4.0]]], ["Constant", [1.0]],
+             [3.0, 1.0, 0.5, 0.2, 0.7, 0.1], [2.0, 0.4, 0.6], [2.0, 0.4, 0.6],
+             [["Constant", [12.0]], None, ["Constant", [0.0]]])):
+        d = data[dname]
+        p = d["y"].shape[0]
+        nodes = [build(ref_node, sp) for sp in nspecs]
+        means = [build(ref_mean, sp) for sp in mspecs]
+        args = []
+        for i in range(p):
+            args += [d["y"][i].copy(), d["yerr"][i].copy()]
+        anet = ref_art_network(nodes, [build(ref_weight, wspec)], list(wvals), means, list(ctor_jit), d["time"].copy(), *args)
+        ll = float(anet.log_likelihood(nodes, [build(ref_weight, wspec)], list(wvals), means, list(call_jit)))
+        tsx = np.linspace(d["time"].min() - 2, d["time"].max() + 2, 37)
+        entry = {"name": name, "data": dname, "nodes": nspecs, "weight": wspec, "weights_values": wvals,
+                 "ctor_jitters": ctor_jit, "jitters": call_jit, "means": mspecs, "ll": ll, "datasets": []}
+        for ds in range(1, p + 1):
+            mu, sd, cov = anet.prediction(nodes=nodes, weights=[build(ref_weight, wspec)], weights_values=list(wvals),
+                                          means=means, jitters=list(call_jit), time=tsx.copy(), dataset=ds)
+            key = "%s_ds%d" % (name, ds)
+            arrays[key + "_tstar"], arrays[key + "_mean"], arrays[key + "_std"], arrays[key + "_cov"] = tsx, mu, sd, np.array(cov)
+            entry["datasets"].append(ds)
+        arrays[name + "_compute"] = anet.compute_matrix(nodes, build(ref_weight, wspec), list(wvals), d["time"])
+        cases["legacy_art"].append(entry)
+        print(name, ll)
 
     flat = {}
     for k, d in data.items():
