@@ -105,6 +105,16 @@ struct agpn_ctx {
     cudaEvent_t ev_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+// owning device allocation for the short-lived buffers of the test / API helpers (freed on every path)
+struct DevBuf {
+    double* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(double) * n); }
+};
+
 static double host_mean(const double* t, int n) {
     long double s = 0.0L;
     for (int i = 0; i < n; ++i) s += t[i];
@@ -665,15 +675,16 @@ extern "C" int agpn_mean_table(agpn_ctx* c, const double* theta, const double* t
     if (!t) n = c->N;
     if (n < 1) USAGE_FAIL("agpn_mean_table: empty grid");
     CUDA_TRY(cudaSetDevice(c->device));
-    double *d_th = nullptr, *d_t = nullptr, *d_o = nullptr;
-    CUDA_TRY(cudaMalloc(&d_th, sizeof(double) * c->S.D));
-    CUDA_TRY(cudaMalloc(&d_o, sizeof(double) * (size_t)c->p * n));
+    DevBuf b_th, b_t, b_o;
+    CUDA_TRY(b_th.alloc(c->S.D));
+    CUDA_TRY(b_o.alloc((size_t)c->p * n));
+    double *d_th = b_th.p, *d_o = b_o.p;
     CUDA_TRY(cudaMemcpy(d_th, theta, sizeof(double) * c->S.D, cudaMemcpyHostToDevice));
     MeanArgs m;
     if (t) {
-        CUDA_TRY(cudaMalloc(&d_t, sizeof(double) * n));
-        CUDA_TRY(cudaMemcpy(d_t, t, sizeof(double) * n, cudaMemcpyHostToDevice));
-        m.t = d_t; m.tmean = host_mean(t, n); m.t0 = t[0];
+        CUDA_TRY(b_t.alloc(n));
+        CUDA_TRY(cudaMemcpy(b_t.p, t, sizeof(double) * n, cudaMemcpyHostToDevice));
+        m.t = b_t.p; m.tmean = host_mean(t, n); m.t0 = t[0];
     } else {
         m.t = c->d_t; m.tmean = c->tmean; m.t0 = c->t0;
     }
@@ -682,7 +693,6 @@ extern "C" int agpn_mean_table(agpn_ctx* c, const double* theta, const double* t
     mean_kernel<<<dim3(c->p, 1), 256>>>(c->S, m);
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpy(out, d_o, sizeof(double) * (size_t)c->p * n, cudaMemcpyDeviceToHost));
-    cudaFree(d_th); cudaFree(d_o); cudaFree(d_t);
     return 0;
 }
 
@@ -901,26 +911,25 @@ extern "C" int agpn_kernel_eval(int device, int family, int kind, const double* 
     if (!nonstat && !r) USAGE_FAIL("agpn_kernel_eval: stationary kernels need r");
     CUDA_TRY(cudaSetDevice(device));
     const size_t n = (size_t)rows * cols;
-    double *d_r = nullptr, *d_t1 = nullptr, *d_t2 = nullptr, *d_o = nullptr;
-    CUDA_TRY(cudaMalloc(&d_o, sizeof(double) * n));
+    DevBuf b_r, b_t1, b_t2, b_o;
+    CUDA_TRY(b_o.alloc(n));
     if (r) {
-        CUDA_TRY(cudaMalloc(&d_r, sizeof(double) * n));
-        CUDA_TRY(cudaMemcpy(d_r, r, sizeof(double) * n, cudaMemcpyHostToDevice));
+        CUDA_TRY(b_r.alloc(n));
+        CUDA_TRY(cudaMemcpy(b_r.p, r, sizeof(double) * n, cudaMemcpyHostToDevice));
     }
     if (t1) {
-        CUDA_TRY(cudaMalloc(&d_t1, sizeof(double) * rows));
-        CUDA_TRY(cudaMemcpy(d_t1, t1, sizeof(double) * rows, cudaMemcpyHostToDevice));
+        CUDA_TRY(b_t1.alloc(rows));
+        CUDA_TRY(cudaMemcpy(b_t1.p, t1, sizeof(double) * rows, cudaMemcpyHostToDevice));
     }
     if (t2) {
-        CUDA_TRY(cudaMalloc(&d_t2, sizeof(double) * cols));
-        CUDA_TRY(cudaMemcpy(d_t2, t2, sizeof(double) * cols, cudaMemcpyHostToDevice));
+        CUDA_TRY(b_t2.alloc(cols));
+        CUDA_TRY(cudaMemcpy(b_t2.p, t2, sizeof(double) * cols, cudaMemcpyHostToDevice));
     }
     const PKern k = prep_kernel(family, kind, pars);
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
-    kernel_eval_kernel<<<blocks, 256>>>(k, d_r, d_t1, d_t2, rows, cols, square_quirk, d_o);
+    kernel_eval_kernel<<<blocks, 256>>>(k, b_r.p, b_t1.p, b_t2.p, rows, cols, square_quirk, b_o.p);
     LAUNCH_CHECK();
-    CUDA_TRY(cudaMemcpy(out, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    cudaFree(d_r); cudaFree(d_t1); cudaFree(d_t2); cudaFree(d_o);
+    CUDA_TRY(cudaMemcpy(out, b_o.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return 0;
 }
 

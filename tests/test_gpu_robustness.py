@@ -129,3 +129,33 @@ def test_prediction_small_grids_and_training_grid():
         emu, esd = oracle.prediction(d["time"], d["y"], d["yerr"], case["q"], onodes, oweights, omeans, case["jitters"], ts, 3)
         assert np.max(np.abs(mu - emu)) <= 1e-9 * np.max(np.abs(emu))
         assert np.max(np.abs(sd ** 2 - esd ** 2)) <= 1e-9 * np.max(esd ** 2)
+
+
+def test_integration_md_ctypes_stub_runs():
+    """The ctypes stub printed in INTEGRATION.md (section B) is executed verbatim against the built library
+    with kernel objects that only expose a class name and .pars (what the reference's objects expose)."""
+    import os
+    import re
+    from artgpn_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# artgpn/_b200\.py.*?)```", md, re.S).group(1)
+    code = code.replace('ctypes.CDLL("libartgpn_b200.so")', 'ctypes.CDLL(%r)' % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+
+    def obj(name, pars):
+        return type(name, (), {"pars": list(pars)})()
+    case = H.loglike_case("G4_sun50_initial")
+    d = H.dataset(case["data"])
+    fake_net = type("network", (), {"time": d["time"], "y": d["y"], "yerr": d["yerr"], "p": 3, "q": 1})()
+    be = ns["B200Backend"](fake_net)
+    nodes = [obj(s[0], s[1]) for s in case["nodes"]]
+    weights = [obj(s[0], s[1]) for s in case["weights"]]
+    means = [obj(s[0], s[1]) for s in case["means"]]
+    ll = be.log_likelihood(nodes, weights, means, case["jitters"])
+    assert abs(ll - case["ll"]) <= LL_RTOL * abs(case["ll"])
+    a = H.arrays()
+    mu, sd, _ = be.prediction(nodes, weights, means, case["jitters"], a["pred_G4_ds2_tstar"], 2)
+    assert np.max(np.abs(mu - a["pred_G4_ds2_mean"])) <= 1e-9 * np.max(np.abs(a["pred_G4_ds2_mean"]))
+    assert np.max(np.abs(sd ** 2 - a["pred_G4_ds2_std"] ** 2)) <= 1e-9 * np.max(a["pred_G4_ds2_std"] ** 2)
