@@ -34,6 +34,8 @@ _SIGNATURES = {
     "agpn_mean_table": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, c_void_p]),
     "agpn_predict": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
+    "agpn_predict_slice": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, ctypes.c_double,
+                                          ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agpn_predict_cov": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, ctypes.c_double,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "agpn_kernel_eval": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p,

@@ -372,6 +372,26 @@ class network(object):
             raise ValueError("array must not contain infs or NaNs")
         return mu, sd, time
 
+    def prediction_slice(self, nodes, weights, means, jitters, time, lo, hi, dataset=1):
+        """Mean / std of the grid points time[lo:hi] of a larger prediction grid `time` (building block of
+        sharding.prediction_sharded; see agpn_predict_slice for the two cases it does not cover)."""
+        time = np.ascontiguousarray(time, dtype=np.float64)
+        s = Structure(self.p, self.q, nodes, weights, means)
+        self._apply_structure(s)
+        theta = s.pack(nodes, weights, means, jitters)
+        ts = np.ascontiguousarray(time[lo:hi])
+        mu, sd = np.empty(ts.size), np.empty(ts.size)
+        status = np.zeros(1, dtype=np.int32)
+        if ts.size:
+            _lib.check(_lib.load().agpn_predict_slice(self._ctx(), _lib.ptr(theta), dataset - 1, ts.size, _lib.ptr(ts),
+                                                      float(time.mean()), float(time[0]), _lib.ptr(mu), _lib.ptr(sd),
+                                                      _lib.ptr(status), None))
+        if status[0] == STATUS_NOT_PD:
+            raise np.linalg.LinAlgError("matrix is not positive definite")
+        if status[0] == STATUS_NOT_FINITE:
+            raise ValueError("array must not contain infs or NaNs")
+        return mu, sd
+
     def prediction_cov(self, nodes=None, weights=None, means=None, jitters=None, time=None, dataset=1,
                        train_jitter=None):
         """

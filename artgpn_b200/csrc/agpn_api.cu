@@ -696,8 +696,22 @@ extern "C" int agpn_mean_table(agpn_ctx* c, const double* theta, const double* t
     return 0;
 }
 
+static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, const double* tstar, bool have_grid,
+                        double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status, void* stream);
+
 extern "C" int agpn_predict(agpn_ctx* c, const double* theta, int series, int M, const double* tstar,
                             double* mean_out, double* std_out, int* status, void* stream) {
+    return predict_impl(c, theta, series, M, tstar, false, 0.0, 0.0, mean_out, std_out, status, stream);
+}
+
+extern "C" int agpn_predict_slice(agpn_ctx* c, const double* theta, int series, int M, const double* tstar,
+                                  double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status,
+                                  void* stream) {
+    return predict_impl(c, theta, series, M, tstar, true, grid_mean, grid_t0, mean_out, std_out, status, stream);
+}
+
+static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, const double* tstar, bool have_grid,
+                        double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status, void* stream) {
     if (!c || !theta || !tstar || !mean_out || !std_out) USAGE_FAIL("agpn_predict: null pointer");
     if (!c->has_structure) USAGE_FAIL("agpn_predict: call agpn_set_structure first");
     if (series < 0 || series >= c->p) USAGE_FAIL("agpn_predict: series out of range");
@@ -747,7 +761,8 @@ extern "C" int agpn_predict(agpn_ctx* c, const double* theta, int series, int M,
     mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
     LAUNCH_CHECK();
     // mean on the prediction grid (arttwo.py:388): centred on / anchored at the prediction grid itself
-    m.t = d_ts; m.n = M; m.n_pad = M; m.tmean = host_mean(tstar, M); m.t0 = tstar[0]; m.y = nullptr; m.out = d_ms;
+    m.t = d_ts; m.n = M; m.n_pad = M; m.tmean = have_grid ? grid_mean : host_mean(tstar, M);
+    m.t0 = have_grid ? grid_t0 : tstar[0]; m.y = nullptr; m.out = d_ms;
     m.subtract = 0; m.rflag = nullptr;
     mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
     LAUNCH_CHECK();

@@ -62,3 +62,31 @@ def log_likelihood_batch_sharded(net, theta, group=None, evaluator=None):
     else:
         local = evaluator(mine)
     return gather_loglikes(local, W, group)
+
+
+def prediction_sharded(net, nodes, weights, means, jitters, time, dataset=1, group=None):
+    """network.prediction with the prediction grid split over the ranks: every rank
+    factorises the same training block (cheap next to the N^2 M solve), predicts its contiguous slice of
+    `time` and one all-gather returns the full (mean, std, time) on every rank.  mean.Linear / Keplerian
+    see the statistics of the WHOLE grid.  Restrictions: see agpn_predict_slice."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    time = np.ascontiguousarray(time, dtype=np.float64)
+    M = time.size
+    lo, hi = shard_bounds(M, world, rank)
+    mu, sd = net.prediction_slice(nodes, weights, means, jitters, time, lo, hi, dataset)
+    dev = torch.device("cuda", net._device)
+    both = torch.from_numpy(np.concatenate([mu, sd])).to(dev) if hi > lo else torch.empty(0, dtype=torch.float64, device=dev)
+    sizes = shard_sizes(M, world)
+    mx = max(sizes)
+    pad = torch.full((2 * mx,), float("nan"), dtype=torch.float64, device=dev)
+    n = hi - lo
+    pad[:n] = both[:n]
+    pad[mx:mx + n] = both[n:]
+    buf = torch.empty(2 * mx * world, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    buf = buf.cpu().numpy().reshape(world, 2, mx)
+    y_mean = np.concatenate([buf[r, 0, :sizes[r]] for r in range(world)])
+    y_std = np.concatenate([buf[r, 1, :sizes[r]] for r in range(world)])
+    return y_mean, y_std, time

@@ -115,6 +115,17 @@ int agpn_predict(agpn_ctx* ctx, const double* theta, int series, int M, const do
                  double* mean_out, double* std_out, int* status, void* stream);
 
 /*
+ * agpn_predict for a SLICE of a larger prediction grid (multi-GPU: the grid is split over ranks, SURVEY
+ * section 8(e)).  mean.Linear is centred on the mean of the WHOLE grid and mean.Keplerian anchored at its
+ * first point (mean.py:92,175), so both are passed in.  Not valid for a Keplerian mean whose "any |M1| >
+ * 1e-10" test (mean.py:180) would differ between the slice and the whole grid, nor for WhiteNoise kernels
+ * when the whole grid has exactly N points (the square-lag quirk is evaluated per slice).
+ */
+int agpn_predict_slice(agpn_ctx* ctx, const double* theta, int series, int M, const double* tstar,
+                       double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status,
+                       void* stream);
+
+/*
  * Predictive mean AND full covariance (what y_cov of arttwo.py:393 / the legacy art.py:350-354 hold):
  * cov_out[M][M] = K** + s^2 I - K* K^-1 K*^T, mean_out[M] as agpn_predict.  Computed as the Schur
  * complement of a partial blocked Cholesky of the augmented matrix [K . ; K* K**] with the same
