@@ -61,3 +61,22 @@ def test_c3_se_weights_one_walker_vs_oracle():
     m = M()
     exp = oracle.log_likelihood(t, y, sig, 2, *synth.objects_from_row(m, m, m, theta[1], 3, 2, "SquaredExponential"))
     assert abs(got - exp) <= 1e-9 * abs(exp), (got, exp)
+
+
+def test_ragged_3000_points_three_groups_vs_oracle():
+    """N = 3000 (24 block columns = three groups of 8, ragged last tile), 2 walkers, SE weights."""
+    from artgpn_b200 import synth, node, weight, mean
+    from artgpn_b200.arttwo import network
+    t, y, sig = synth.make_data(3000, 2, seed=3)
+    theta = synth.make_walkers(2, p=2, q=2, weights="SquaredExponential", seed=4)
+    net = network(2, t, y[0], sig[0], y[1], sig[1])
+    net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], 2, 2, "SquaredExponential")[:3])
+    got = net.log_likelihood_batch(theta)
+
+    class M(object):
+        def __getattr__(self, name):
+            return lambda *pars: (name, list(pars))
+    m = M()
+    for w in range(2):
+        exp = oracle.log_likelihood(t, y, sig, 2, *synth.objects_from_row(m, m, m, theta[w], 2, 2, "SquaredExponential"))
+        assert abs(got[w] - exp) <= 1e-9 * abs(exp), (w, got[w], exp)
