@@ -390,8 +390,9 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
 static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor, int kstop = -1) {
     size_t local_cursor = 0;
     size_t& cur = cursor ? *cursor : local_cursor;
-    // few matrices: the left-looking narrow updates of a deep group have too few CTAs to fill the GPU
-    // (measured: 12 matrices of 2048^2 -> group 2 is 7 % faster than 8; >= 48 matrices -> 8 is best)
+    // few small matrices: the left-looking narrow updates of a deep group have too few CTAs to fill the GPU
+    // (measured: 12 matrices of 2048^2 -> group 2 is 7 % faster than 8; 48 of 2048^2 or 12 of 8192^2 -> 8);
+    // callers set group_eff from matrices x block columns
     const int group = c->group_eff < 1 ? 1 : c->group_eff;
     // kstop < nblk: partial factorisation -- only the first kstop block columns are eliminated; the
     // remaining trailing block then holds the Schur complement (used for the predictive covariance)
@@ -570,7 +571,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
         g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
         g.info = d_infoflag;
         g.A0 = c->d_A; g.mat0 = 0;
-        c->group_eff = (c->group_fixed || nmat >= 24) ? c->group : 2;
+        c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
         const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
         if (nsub == 1) {
             if (run_cholesky(c, g, st, &cur)) return 1;
@@ -971,7 +972,7 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     g.A0 = A; g.mat0 = 0;
     if (const char* e = getenv("AGPN_SYRK")) { tmp.use_tma = strncmp(e, "tma", 3) == 0; tmp.tma_mc = strcmp(e, "tma_nomc") != 0; }
     tmp.maps_valid = tmp.use_tma && make_batch_map(&tmp.tmA, A, nmat, n_pad, n_pad, TB) && make_batch_map(&tmp.tmB, A, nmat, n_pad, n_pad, BN);
-    tmp.group_eff = (tmp.group_fixed || nmat >= 24) ? tmp.group : 2;
+    tmp.group_eff = (tmp.group_fixed || (long long)nmat * (n_pad / TB) >= 384) ? tmp.group : 2;
     int rc = run_cholesky(&tmp, g, st, nullptr);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(d_linv);
