@@ -26,6 +26,7 @@ _SIGNATURES = {
     "agpn_destroy": (ctypes.c_int, [c_void_p]),
     "agpn_set_structure": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int]),
     "agpn_theta_dim": (ctypes.c_int, [c_void_p]),
+    "agpn_set_exact": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "agpn_loglike_batch": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, ctypes.c_int, c_void_p,
                                           ctypes.c_int, c_void_p, c_void_p]),
     "agpn_covariance_block": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, c_void_p, ctypes.c_int,

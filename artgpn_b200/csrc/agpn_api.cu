@@ -97,6 +97,7 @@ struct agpn_ctx {
     int group_eff = 8;         // group used by the current call (set from the TOTAL number of matrices)
     bool no_fast_asm = false;  // AGPN_GENERIC_ASM=1 forces the generic assembly kernel
     bool no_small = false;     // AGPN_NO_SMALL=1 disables the fused small-N kernel
+    bool exact = false;        // agpn_set_exact: reference operation order in every kernel evaluation
     // sub-batch streams: the matrices of a batch are split over nsub streams so that one sub-batch's
     // small serial kernels (diagonal block, panel solve) overlap another's wide tensor update
     int nsub = 6;              // AGPN_STREAMS
@@ -299,6 +300,12 @@ extern "C" int agpn_set_structure(agpn_ctx* c, const int* node_kind, const int* 
 
 extern "C" int agpn_theta_dim(const agpn_ctx* c) { return (c && c->has_structure) ? c->S.D : -1; }
 
+extern "C" int agpn_set_exact(agpn_ctx* c, int enable) {
+    if (!c) USAGE_FAIL("agpn_set_exact: null context");
+    c->exact = enable != 0;
+    return 0;
+}
+
 extern "C" int agpn_set_profiling(agpn_ctx* c, int enable) {
     if (!c) USAGE_FAIL("agpn_set_profiling: null context");
     c->profiling = enable != 0;
@@ -436,7 +443,7 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
 // QuasiPeriodic and every weight Constant / SE (the reference's example networks and the bench)
 static bool fast_assembly_ok(const agpn_ctx* c, const AsmArgs& a, bool* wse) {
     if (!a.lower_only || !a.square || !a.add_err || !a.add_jit || !a.pad_identity || !a.vec2) return false;
-    if (c->no_fast_asm || c->S.q > ASMF_MAXQ || a.nser > 4 || a.rows_out % ASM_TILE || a.cols_out != a.rows_out) return false;
+    if (c->no_fast_asm || c->exact || c->S.q > ASMF_MAXQ || a.nser > 4 || a.rows_out % ASM_TILE || a.cols_out != a.rows_out) return false;
     *wse = false;
     for (int j = 0; j < c->S.q; ++j) {
         const int k = c->S.node_kind[j];
@@ -542,7 +549,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
             PhaseScope ps(c, st, PH_ASM, cur);
             AsmArgs probe;
             probe.lower_only = 1; probe.square = 1; probe.add_err = 1; probe.add_jit = 1; probe.pad_identity = 1; probe.vec2 = 1;
-            probe.nser = 1; probe.rows_out = c->npad; probe.cols_out = c->npad; probe.series0 = 0;
+            probe.nser = 1; probe.rows_out = c->npad; probe.cols_out = c->npad; probe.series0 = 0; probe.exact = 0;
             bool wse = false, fast = true;
             for (int s = 0; s < p && fast; ++s) {
                 probe.series0 = s;
@@ -550,7 +557,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
             }
             SmallArgs sa;
             sa.theta = d_theta; sa.t = c->d_t; sa.yerr = c->d_yerr; sa.rhs = c->d_rhs; sa.rhs_stride = c->npad;
-            sa.N = c->N; sa.nb = small_nb; sa.fast = fast ? 1 : 0; sa.torigin = c->t0;
+            sa.N = c->N; sa.nb = small_nb; sa.fast = (fast && !c->exact) ? 1 : 0; sa.exact = c->exact ? 1 : 0; sa.torigin = c->t0;
             sa.logdet = c->d_logdet; sa.quad = c->d_quad; sa.info = d_infoflag; sa.kflag = d_kflag;
             const size_t smem = small_smem_bytes(small_nb, c->q);    // <= 227 KB for nb <= 12, q <= 8 (attribute set at create)
             small_fused_kernel<<<dim3(p, Ww), 256, smem, st>>>(c->S, sa);
@@ -563,7 +570,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
             a.rows_out = c->npad; a.cols_out = c->npad; a.yerr = c->d_yerr; a.out = c->d_A;
             a.mat_stride = (long long)(np * np); a.ld = c->npad; a.series0 = 0; a.nser = p;
             a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1;
-            a.use_trig = 1; a.vec2 = 1; a.torigin = c->t0; a.kflag = d_kflag;
+            a.use_trig = 1; a.vec2 = 1; a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
             if (launch_assemble(c, a, Ww, st)) return 1;
         }
         CholArgs g;
@@ -660,7 +667,7 @@ extern "C" int agpn_covariance_block(agpn_ctx* c, const double* theta, int serie
     a.yerr = c->d_yerr; a.out = d_out; a.mat_stride = (long long)na * nb; a.ld = nb; a.series0 = series; a.nser = 1;
     a.lower_only = 0; a.square = square_quirk ? 1 : 0; a.add_err = add_errors ? 1 : 0; a.add_jit = 0;
     a.pad_identity = 0; a.use_trig = 0; a.vec2 = ((nb % 2) == 0 && ((uintptr_t)d_out % 16) == 0) ? 1 : 0;
-    a.torigin = c->t0; a.kflag = nullptr;
+    a.torigin = c->t0; a.kflag = nullptr; a.exact = c->exact ? 1 : 0;
     rc = launch_assemble(c, a, 1, st);
     if (rc == 0 && !out_on_device)
         CB_TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)na * nb, cudaMemcpyDeviceToHost, st));
@@ -772,7 +779,7 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
     a.theta = c->d_theta; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
     a.yerr = c->d_yerr; a.out = c->d_A; a.mat_stride = (long long)(np * np); a.ld = c->npad; a.series0 = series; a.nser = 1;
     a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1; a.use_trig = 1; a.vec2 = 1;
-    a.torigin = c->t0; a.kflag = d_kflag;
+    a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
     if (launch_assemble(c, a, 1, st)) return 1;
     CholArgs g;
     g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = 1;
@@ -785,7 +792,7 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
     LAUNCH_CHECK();
     PredArgs pa;
     pa.theta = c->d_theta; pa.tstar = d_ts; pa.ttrain = c->d_t; pa.M = M; pa.N = c->N; pa.n_pad = c->npad; pa.nblk = c->nblk;
-    pa.series = series; pa.square = (M == c->N) ? 1 : 0; pa.L = c->d_A; pa.ld = c->npad; pa.Linv = c->d_LinvAll;
+    pa.series = series; pa.square = (M == c->N) ? 1 : 0; pa.exact = c->exact ? 1 : 0; pa.L = c->d_A; pa.ld = c->npad; pa.Linv = c->d_LinvAll;
     pa.z = c->d_rhs; pa.V = c->d_V; pa.mstar = d_ms; pa.kss = d_kss; pa.mean_out = d_mu; pa.std_out = d_sd;
     predict_kernel<<<(unsigned)(Mpad / TB), 256, GEMM_SMEM_BYTES, st>>>(c->S, pa);
     LAUNCH_CHECK();
@@ -878,7 +885,7 @@ extern "C" int agpn_predict_cov(agpn_ctx* c, const double* theta, int series, in
     a.theta = d_th + D; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
     a.yerr = c->d_yerr; a.out = c->d_aug; a.mat_stride = (long long)(T * T); a.ld = (int)T; a.series0 = series; a.nser = 1;
     a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1; a.use_trig = 1; a.vec2 = 1;
-    a.torigin = c->t0; a.kflag = d_kflag;
+    a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
     if (launch_assemble(c, a, 1, st)) return 1;
     a.theta = d_th; a.ta = d_ts; a.tb = c->d_t; a.na = M; a.nb = c->N; a.rows_out = (int)Mpad; a.cols_out = c->npad;
     a.out = c->d_aug + npad * T; a.lower_only = 0; a.square = (M == c->N) ? 1 : 0; a.add_err = 0; a.add_jit = 0;

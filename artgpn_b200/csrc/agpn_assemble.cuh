@@ -33,6 +33,7 @@ struct AsmArgs {
     int pad_identity;        // entries outside [na][nb]: 1 on the diagonal, else 0
     int use_trig;            // angle-addition tables for node kernels with a sin term
     int vec2;                // 16-byte stores allowed
+    int exact;               // reference operation order, no hoisting / tables / fma (kern_value_exact)
     double torigin;          // phase origin of the tables
     int* kflag;              // [W * nser] set to 1 if a produced entry is not finite (or nullptr)
 };
@@ -44,6 +45,9 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
     __shared__ double s_ta[ASM_TILE], s_tb[ASM_TILE];
     __shared__ double s_diag[AGPN_MAXP][ASM_TILE];
     __shared__ double s_trig[ASM_NTRIG][4][ASM_TILE];   // [slot][sin row, cos row, sin col, cos col]
+    // exact mode: raw parameters alias the table storage (tables are not used then)
+    RKern* s_rnode = reinterpret_cast<RKern*>(&s_trig[0][0][0]);
+    RKern* s_rweight = s_rnode + AGPN_MAXQ;
 
     const int tid = threadIdx.x;
     const int w = blockIdx.y;
@@ -66,17 +70,19 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
     // ---- per-CTA preparation -------------------------------------------------------------------
     if (tid < q) {
         s_node[tid] = prep_kernel(0, S.node_kind[tid], th + S.node_off[tid]);
+        if (g.exact) s_rnode[tid] = prep_raw(0, S.node_kind[tid], th + S.node_off[tid]);
     } else if (tid >= 32 && tid < 32 + g.nser * q) {
         const int u = tid - 32;
         const int s = u / q, j = u % q;
         const int widx = j + q * (g.series0 + s);
         s_weight[u] = prep_kernel(1, S.weight_kind[widx], th + S.weight_off[widx]);
+        if (g.exact) s_rweight[u] = prep_raw(1, S.weight_kind[widx], th + S.weight_off[widx]);
     }
     if (tid == 64) {
         int slot = 0;
         for (int j = 0; j < AGPN_MAXQ; ++j) {
             int v = -1;
-            if (j < q && g.use_trig && kernel_has_sin(S.node_kind[j]) && slot < ASM_NTRIG) v = slot++;
+            if (j < q && g.use_trig && !g.exact && kernel_has_sin(S.node_kind[j]) && slot < ASM_NTRIG) v = slot++;
             s_slot[j] = v;
         }
     }
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
         }
     }
     __syncthreads();
-    if (g.use_trig) {
+    if (g.use_trig && !g.exact) {
         for (int j = 0; j < q; ++j) {
             const int slot = s_slot[j];
             if (slot < 0) continue;
@@ -144,7 +150,10 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
             if (j < q) {
                 const PKern& kn = s_node[j];
                 const int slot = s_slot[j];
-                if (slot >= 0) {
+                if (g.exact) {
+                    F0[j] = kern_value_exact(s_rnode[j], r0, t1, tb0, dg0);
+                    F1[j] = kern_value_exact(s_rnode[j], r1, t1, tb1, dg1);
+                } else if (slot >= 0) {
                     const double sr = s_trig[slot][0][row], cr = s_trig[slot][1][row];
                     const double sa = sr * s_trig[slot][3][c0] - cr * s_trig[slot][2][c0];
                     const double sb = sr * s_trig[slot][3][c0 + 1] - cr * s_trig[slot][2][c0 + 1];
@@ -166,7 +175,10 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
             for (int j = 0; j < AGPN_MAXQ; ++j) {
                 if (j < q) {
                     const PKern& kw = s_weight[s * q + j];
-                    if (kw.kind == K_CONSTANT) {
+                    if (g.exact) {          // k_ii = k_ii + (w * f_hat), one rounding per operation (arttwo.py:279)
+                        v0 = __dadd_rn(v0, __dmul_rn(kern_value_exact(s_rweight[s * q + j], r0, t1, tb0, dg0), F0[j]));
+                        v1 = __dadd_rn(v1, __dmul_rn(kern_value_exact(s_rweight[s * q + j], r1, t1, tb1, dg1), F1[j]));
+                    } else if (kw.kind == K_CONSTANT) {
                         v0 = fma(kw.amp, F0[j], v0);
                         v1 = fma(kw.amp, F1[j], v1);
                     } else {

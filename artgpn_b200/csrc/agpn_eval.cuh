@@ -193,6 +193,106 @@ __device__ __noinline__ double kern_shape(const PKern& k, double r, double t1, d
     }
 }
 
+// ---- "exact" evaluation: the reference's own operation order, one IEEE rounding per numpy operation
+// (explicit __d*_rn intrinsics: no hoisted reciprocals, no fma contraction).  Entries then agree with
+// numpy up to the last-ulp differences between libdevice and glibc sin / cos / exp / pow.  Used when
+// parity is wanted on ill-conditioned covariances, where a 1e-14 relative difference in K is amplified
+// by cond(K) in the log-likelihood.  ~4x slower than the hoisted form.
+struct RKern {
+    int kind;
+    int family;
+    double w2;        // weight**2 (weight kernels), else 1
+    double h[4];      // remaining .pars in constructor order
+};
+
+__host__ __device__ inline RKern prep_raw(int family, int kind, const double* pars) {
+    RKern k;
+    k.kind = kind;
+    k.family = family;
+    k.w2 = 1.0;
+    const double* h = pars;
+    if (family == 1 && kind != K_CONSTANT && kind != K_WHITENOISE) {
+        k.w2 = pars[0] * pars[0];
+        h = pars + 1;
+    }
+    const int n = kernel_npars(0, kind);
+    for (int i = 0; i < 4; ++i) k.h[i] = i < n ? h[i] : 0.0;
+    return k;
+}
+
+__device__ __noinline__ double kern_value_exact(const RKern& k, double r, double t1, double t2, bool on_diag) {
+    const double ar = fabs(r);
+    const double* h = k.h;
+    const bool wt = k.family == 1;
+    double shape;
+    switch (k.kind) {
+        case K_CONSTANT:                    // node: c ; weight: c**2
+            return wt ? __dmul_rn(h[0], h[0]) : h[0];
+        case K_WHITENOISE:
+            return on_diag ? __dmul_rn(h[0], h[0]) : 0.0;
+        case K_SE:                          // exp(-0.5 * r**2 / ell**2)
+            shape = exp(__ddiv_rn(__dmul_rn(-0.5, __dmul_rn(r, r)), __dmul_rn(h[0], h[0])));
+            break;
+        case K_PERIODIC: {                  // exp(-2 * sin(pi*|r|/P)**2 / ell**2)
+            const double sn = sin(__ddiv_rn(__dmul_rn(AGPN_PI, ar), h[0]));
+            shape = exp(__ddiv_rn(__dmul_rn(-2.0, __dmul_rn(sn, sn)), __dmul_rn(h[1], h[1])));
+            break;
+        }
+        case K_QP: {                        // exp(-2*sin(pi*|r|/P)**2/ell_p**2 - r**2/(2*ell_e**2))
+            const double sn = sin(__ddiv_rn(__dmul_rn(AGPN_PI, ar), h[1]));
+            const double a = -__ddiv_rn(__dmul_rn(2.0, __dmul_rn(sn, sn)), __dmul_rn(h[2], h[2]));
+            const double b = __ddiv_rn(__dmul_rn(r, r), __dmul_rn(2.0, __dmul_rn(h[0], h[0])));
+            shape = exp(__dsub_rn(a, b));
+            break;
+        }
+        case K_RQ: {                        // 1 / (1 + r**2/(2*alpha*ell**2))**alpha
+            const double base = __dadd_rn(1.0, __ddiv_rn(__dmul_rn(r, r), __dmul_rn(__dmul_rn(2.0, h[0]), __dmul_rn(h[1], h[1]))));
+            const double pw = pow(base, h[0]);
+            return wt ? __ddiv_rn(k.w2, pw) : __ddiv_rn(1.0, pw);
+        }
+        case K_RQP: {                       // pars (alpha, ell_e, P, ell_p)
+            const double sn = sin(__ddiv_rn(__dmul_rn(AGPN_PI, ar), h[2]));
+            const double e = exp(-__ddiv_rn(__dmul_rn(2.0, __dmul_rn(sn, sn)), __dmul_rn(h[3], h[3])));
+            const double b = __dadd_rn(1.0, __ddiv_rn(__dmul_rn(r, r), __dmul_rn(__dmul_rn(2.0, h[0]), __dmul_rn(h[1], h[1]))));
+            if (wt) return __ddiv_rn(__dmul_rn(k.w2, e), pow(b, h[0]));
+            const double sg = (b > 0.0) ? 1.0 : ((b < 0.0) ? -1.0 : 0.0);
+            return __ddiv_rn(e, __dmul_rn(sg, pow(fabs(b), h[0])));
+        }
+        case K_COSINE:                      // cos(2*pi*|r| / P)
+            shape = cos(__ddiv_rn(__dmul_rn(2.0 * AGPN_PI, ar), h[0]));
+            break;
+        case K_EXP:                         // exp(-|r|/ell)
+            shape = exp(__ddiv_rn(-ar, h[0]));
+            break;
+        case K_M32: {                       // (1 + sqrt3*|r|/ell) * exp(-sqrt3*|r|/ell)
+            const double s3 = 1.7320508075688772;
+            const double poly = __dadd_rn(1.0, __ddiv_rn(__dmul_rn(s3, ar), h[0]));
+            const double e = exp(__ddiv_rn(__dmul_rn(-s3, ar), h[0]));
+            return wt ? __dmul_rn(__dmul_rn(k.w2, poly), e) : __dmul_rn(poly, e);
+        }
+        case K_M52: {                       // (1 + (3*sqrt5*ell*|r| + 5*|r|**2)/(3*ell**2)) * exp(-sqrt5*|r|/ell)
+            const double s5 = 2.23606797749979;
+            const double num = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(3.0, s5), h[0]), ar), __dmul_rn(5.0, __dmul_rn(ar, ar)));
+            const double poly = __dadd_rn(1.0, __ddiv_rn(num, __dmul_rn(3.0, __dmul_rn(h[0], h[0]))));
+            const double e = exp(__ddiv_rn(__dmul_rn(-s5, ar), h[0]));
+            return wt ? __dmul_rn(__dmul_rn(k.w2, poly), e) : __dmul_rn(poly, e);
+        }
+        case K_LINEAR: {                    // (t1 - c) * (t2 - c)
+            const double a = __dsub_rn(t1, h[0]), b = __dsub_rn(t2, h[0]);
+            return wt ? __dmul_rn(__dmul_rn(k.w2, a), b) : __dmul_rn(a, b);
+        }
+        case K_GAMMAEXP:                    // exp(-(|r|/ell)**gamma), pars (gamma, ell)
+            shape = exp(-pow(__ddiv_rn(ar, h[1]), h[0]));
+            break;
+        case K_POLY:                        // (a*t1*t2 + b)**c
+            shape = pow(__dadd_rn(__dmul_rn(__dmul_rn(h[0], t1), t2), h[1]), h[2]);
+            break;
+        default:
+            return 0.0;
+    }
+    return wt ? __dmul_rn(k.w2, shape) : shape;
+}
+
 // ---- mean functions (mean.py) --------------------------------------------------------------
 // Keplerian first-guess residual M1 (mean.py:175-178); E0 returned through *E0out
 __device__ __forceinline__ double kepler_m1(const double* h, double t, double t0, double* E0out) {

@@ -20,6 +20,7 @@ struct PredArgs {
     int M, N, n_pad, nblk;
     int series;
     int square;              // M == N (WhiteNoise quirk inside K*)
+    int exact;               // reference operation order for the K* entries
     const double* L;         // factor [n_pad][ld]
     int ld;
     const double* Linv;      // [nblk][128][128]
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256, 2) predict_kernel(const __grid_constant__
     extern __shared__ __align__(16) double smem[];
     __shared__ PKern s_node[AGPN_MAXQ];
     __shared__ PKern s_weight[AGPN_MAXQ];
+    __shared__ RKern s_rnode[AGPN_MAXQ], s_rweight[AGPN_MAXQ];
     __shared__ double s_ts[TB], s_tn[TB], s_z[TB];
     __shared__ double s_red[2][2][TB];
     __shared__ __align__(8) unsigned long long bars[2 * GEMM_STAGES];
@@ -44,10 +46,13 @@ __global__ void __launch_bounds__(256, 2) predict_kernel(const __grid_constant__
     const int wm = warp >> 1, wn = warp & 1;
     const int q = S.q;
     const int m0 = blockIdx.x * TB;
-    if (tid < q) s_node[tid] = prep_kernel(0, S.node_kind[tid], g.theta + S.node_off[tid]);
-    else if (tid >= 32 && tid < 32 + q) {
+    if (tid < q) {
+        s_node[tid] = prep_kernel(0, S.node_kind[tid], g.theta + S.node_off[tid]);
+        s_rnode[tid] = prep_raw(0, S.node_kind[tid], g.theta + S.node_off[tid]);
+    } else if (tid >= 32 && tid < 32 + q) {
         const int widx = (tid - 32) + q * g.series;
         s_weight[tid - 32] = prep_kernel(1, S.weight_kind[widx], g.theta + S.weight_off[widx]);
+        s_rweight[tid - 32] = prep_raw(1, S.weight_kind[widx], g.theta + S.weight_off[widx]);
     }
     if (tid < TB) {
         const int gm = m0 + tid;
@@ -85,6 +90,11 @@ __global__ void __launch_bounds__(256, 2) predict_kernel(const __grid_constant__
                             const double r = t1 - t2;
                             const bool dg = g.square && gm == gn;
                             for (int j = 0; j < q; ++j) {
+                                if (g.exact) {
+                                    v = __dadd_rn(v, __dmul_rn(kern_value_exact(s_rweight[j], r, t1, t2, dg),
+                                                               kern_value_exact(s_rnode[j], r, t1, t2, dg)));
+                                    continue;
+                                }
                                 const PKern& kn = s_node[j];
                                 const PKern& kw = s_weight[j];
                                 const double f = kn.kind == K_CONSTANT ? kn.amp : kn.amp * kern_shape(kn, r, t1, t2, dg);

@@ -23,6 +23,7 @@ struct SmallArgs {
     int rhs_stride;
     int N, nb;             // nb = ceil(N / 16)
     int fast;              // exp-family fast formula usable (same rule as assemble_fast_kernel)
+    int exact;             // reference operation order (kern_value_exact); implies !fast
     double torigin;
     double* logdet;        // [W * p]
     double* quad;          // [W * p]
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) small_fused_kernel(const __grid_constant_
     __shared__ PKern s_node[AGPN_MAXQ];
     __shared__ PKern s_weight[AGPN_MAXQ];
     __shared__ double s_fa[AGPN_MAXQ][3];        // fast path: a_j, c_j + cw_j, amp
+    __shared__ RKern s_rnode[AGPN_MAXQ], s_rweight[AGPN_MAXQ];
     __shared__ int s_fail, s_bad;
 
     const int series = blockIdx.x, w = blockIdx.y;
@@ -130,6 +132,8 @@ __global__ void __launch_bounds__(256) small_fused_kernel(const __grid_constant_
         const PKern kw = prep_kernel(1, S.weight_kind[widx], th + S.weight_off[widx]);
         s_node[tid] = kn;
         s_weight[tid] = kw;
+        s_rnode[tid] = prep_raw(0, S.node_kind[tid], th + S.node_off[tid]);
+        s_rweight[tid] = prep_raw(1, S.weight_kind[widx], th + S.weight_off[widx]);
         s_fa[tid][0] = (kn.kind == K_SE) ? 0.0 : kn.a;
         s_fa[tid][1] = ((kn.kind == K_SE) ? kn.a : kn.c) + ((kw.kind == K_SE) ? kw.a : 0.0);
         s_fa[tid][2] = kw.amp;
@@ -171,6 +175,11 @@ __global__ void __launch_bounds__(256) small_fused_kernel(const __grid_constant_
                                               -trig[(2 * j + 1) * np + gi] * trig[(2 * j) * np + gj]);
                         v = fma(s_fa[j][2], exp_nonpos(fma(s_fa[j][1], r2, s_fa[j][0] * sn * sn)), v);
                     }
+                } else if (g.exact) {
+                    const bool dg = gi == gj;
+                    for (int j = 0; j < q; ++j)
+                        v = __dadd_rn(v, __dmul_rn(kern_value_exact(s_rweight[j], rl, t1, t2, dg),
+                                                   kern_value_exact(s_rnode[j], rl, t1, t2, dg)));
                 } else {
                     const bool dg = gi == gj;
                     for (int j = 0; j < q; ++j) {
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(256) small_fused_kernel(const __grid_constant_
                 }
                 if (gi == gj) {
                     const double e = g.yerr[(size_t)series * N + gi];
-                    v += e * e + jt * jt;
+                    v = __dadd_rn(v, __dadd_rn(__dmul_rn(e, e), __dmul_rn(jt, jt)));     // k += (err^2 + jit^2), arttwo.py:280-281
                 }
                 if (!isfinite(v)) bad = 1;
             } else {

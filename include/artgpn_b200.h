@@ -76,6 +76,17 @@ int agpn_set_structure(agpn_ctx* ctx, const int* node_kind, const int* weight_ki
 int agpn_theta_dim(const agpn_ctx* ctx);
 
 /*
+ * Accuracy / speed switch for every covariance entry the context produces afterwards.  enable = 0
+ * (default): divisions hoisted per walker, sin(pi |r| / P) from per-tile angle-addition tables, fused
+ * multiply-adds -- entries agree with the reference to ~1e-13 relative.  enable = 1: the reference's own
+ * operation order with one rounding per numpy operation (node.py / weight.py formulas as written,
+ * arttwo.py:279-281 accumulation) -- entries agree to the last ulp or two (libm differences only), ~4 x
+ * slower assembly.  Matters only for ill-conditioned covariances: a relative difference d in K shows up
+ * as ~ cond(K) * d in the log-likelihood.
+ */
+int agpn_set_exact(agpn_ctx* ctx, int enable);
+
+/*
  * Replaces network.log_likelihood (arttwo.py:240-290) for W parameter rows at once.
  *   theta[W][D], out[W]; *_on_device says whether the pointer is device memory on ctx's device
  *   (else host memory: the copy happens inside the call on `stream`).

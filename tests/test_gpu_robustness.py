@@ -159,3 +159,38 @@ def test_integration_md_ctypes_stub_runs():
     mu, sd, _ = be.prediction(nodes, weights, means, case["jitters"], a["pred_G4_ds2_tstar"], 2)
     assert np.max(np.abs(mu - a["pred_G4_ds2_mean"])) <= 1e-9 * np.max(np.abs(a["pred_G4_ds2_mean"]))
     assert np.max(np.abs(sd ** 2 - a["pred_G4_ds2_std"] ** 2)) <= 1e-9 * np.max(a["pred_G4_ds2_std"] ** 2)
+
+
+def test_exact_mode_entries_and_conditioning():
+    """set_exact(True): covariance entries in the reference's operation order agree with numpy to a few ulp
+    (fast mode: ~1e-13); and parity of the log-likelihood degrades like cond(K) x (entry differences) -- at
+    cond ~ 3e6 both modes stay within 1e-8 of LAPACK, at cond ~ 3e2 within 1e-13."""
+    from artgpn_b200 import node, weight, mean
+    from artgpn_b200.arttwo import network
+    rng = np.random.default_rng(0)
+    N = 300
+    t = 57000.0 + np.sort(rng.uniform(0, 1.0 * N, N))
+    y = rng.normal(0, 2, (3, N))
+    nodes = [node.QuasiPeriodic(18.56, 28.9, 0.7), node.Matern52(9.0)]
+    ws = [weight.Constant(1.99), weight.SquaredExponential(0.7, 40.0), weight.Periodic(4.53, 13.0, 0.9), weight.Constant(1.1),
+          weight.RationalQuadratic(6.94, 1.5, 20.0), weight.Exponential(2.0, 30.0)]
+    ms = [mean.Linear(0.01, 0.1)] * 3
+    sp = lambda k: (type(k).__name__, list(k.pars))
+    for scale, tol in ((1.0, 1e-13), (1e-2, 1e-8)):
+        sig = rng.uniform(0.1, 0.3, (3, N)) * scale
+        jit = [0.8 * scale, 0.37 * scale, 1.06 * scale]
+        exp = oracle.log_likelihood(t, y, sig, 2, [sp(k) for k in nodes], [sp(k) for k in ws], [sp(k) for k in ms], jit)
+        for exact in (False, True):
+            net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2], exact=exact)
+            got = net.log_likelihood(nodes, ws, ms, jit)
+            assert abs(got - exp) <= tol * abs(exp), (scale, exact, got, exp)
+    net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+    for pos in (1, 2, 3):
+        ref = oracle.covariance_block(t, [sp(k) for k in nodes], [sp(k) for k in ws], pos - 1, 2)
+        net.set_exact(False)
+        fast = net._covariance_matrix(nodes, ws, t, pos)
+        net.set_exact(True)
+        exact = net._covariance_matrix(nodes, ws, t, pos)
+        assert np.max(np.abs(fast - ref) / np.abs(ref)) <= 1e-11
+        assert np.max(np.abs(exact - ref) / np.abs(ref)) <= 5e-14
+        assert np.max(np.abs(exact - ref) / np.abs(ref)) <= np.max(np.abs(fast - ref) / np.abs(ref))
