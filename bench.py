@@ -343,7 +343,13 @@ def main():
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "flops_per_launch_group": chol_flops, "ms": chol_ms, "traffic": chol_traffic,
                          "traffic_note": "DRAM bytes of all Cholesky launches of one step, ncu pass in profiles/ (scaled by walkers)",
-                         "syrk_only_tflops": syrk_tf},
+                         "syrk_only_tflops": syrk_tf,
+                         "dominant_kernel": {"kernel": "syrk_kernel (all narrow + wide launches of a step)",
+                                             "executed_tflops": syrk_tf,
+                                             "frac": (syrk_tf / float(peak_tf[0])) if syrk_tf else None,
+                                             "share_of_step_ms": float(phase[4] / max(phase.sum(), 1e-9)),
+                                             "note": "flops actually executed by the tile GEMMs (full diagonal tiles "
+                                                     "counted), CUDA-event time of the syrk launches"}},
             "roofline_assembly": {"bound": "hbm", "kernel": "assemble_fast_kernel (lower block triangle only; generic assemble_kernel for other kernel classes)",
                                   "achieved": asm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                   "frac": asm_gbs / peaks.get("hbm_gbs"), "peak_source": peak_src,
