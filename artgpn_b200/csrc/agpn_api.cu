@@ -103,6 +103,14 @@ struct agpn_ctx {
     int nsub = 6;              // AGPN_STREAMS
     cudaStream_t sub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr;
+    // CUDA-graph replay of one wave (memsets, residual, assembly, all Cholesky launches on all sub-streams,
+    // finalise): ~300 launches per step collapse into one graph launch.  AGPN_GRAPH=0 disables it.
+    bool use_graph = true;
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
+    unsigned long long struct_version = 0, ws_version = 0;
+    struct GraphEntry { int Ww; unsigned long long sv, wv; int exact, group, nsub, tma, mc; cudaGraphExec_t exec; long long nlaunch; };
+    std::vector<GraphEntry> graphs;
     cudaEvent_t ev_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -214,6 +222,11 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
         agpn_destroy(c);
         return 1;
     }
+    if (const char* e = getenv("AGPN_GRAPH")) c->use_graph = atoi(e) != 0;
+    if (cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_gin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_gout, cudaEventDisableTiming) != cudaSuccess)
+        c->use_graph = false;
     if (const char* e = getenv("AGPN_STREAMS")) c->nsub = atoi(e);
     if (c->nsub < 1) c->nsub = 1;
     if (c->nsub > 8) c->nsub = 8;
@@ -242,6 +255,10 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (auto& ge : c->graphs) cudaGraphExecDestroy(ge.exec);
+    if (c->gstream) cudaStreamDestroy(c->gstream);
+    if (c->ev_gin) cudaEventDestroy(c->ev_gin);
+    if (c->ev_gout) cudaEventDestroy(c->ev_gout);
     cudaFree(c->d_t); cudaFree(c->d_y); cudaFree(c->d_yerr);
     cudaFree(c->d_A); cudaFree(c->d_Linv); cudaFree(c->d_rhs); cudaFree(c->d_logdet); cudaFree(c->d_quad);
     cudaFree(c->d_info); cudaFree(c->d_theta); cudaFree(c->d_out); cudaFree(c->d_status);
@@ -295,6 +312,7 @@ extern "C" int agpn_set_structure(agpn_ctx* c, const int* node_kind, const int* 
     S.D = off;
     c->S = S;
     c->has_structure = true;
+    ++c->struct_version;
     return 0;
 }
 
@@ -373,6 +391,7 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 3 * nmat));
         c->cap_mats = nmat;
+        ++c->ws_version;
     }
     if (W > c->cap_w || (size_t)c->S.D > c->cap_D) {
         cudaFree(c->d_theta); cudaFree(c->d_out); cudaFree(c->d_status);
@@ -385,6 +404,7 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_status, sizeof(int) * W));
         c->cap_w = W;
         c->cap_D = D;
+        ++c->ws_version;
     }
     return 0;
 }
@@ -488,6 +508,163 @@ static int launch_assemble(agpn_ctx* c, AsmArgs& a, int W, cudaStream_t st) {
     return 0;
 }
 
+// everything of one wave between "theta is on the device" and "results are in d_out / d_status", enqueued
+// on `st` (plus the sub-batch streams, forked from and joined back into `st`)
+static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_out, cudaStream_t st, size_t& cur) {
+    const int p = c->p;
+    const size_t np = (size_t)c->npad;
+    const int nmat = Ww * p;
+    const double half_n_log2pi = 0.5 * (double)c->N * std::log(2.0 * AGPN_PI);
+    CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double) * nmat, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double) * nmat, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 3 * c->cap_mats, st));
+    int* d_infoflag = c->d_info;
+    int* d_kflag = c->d_info + c->cap_mats;
+    int* d_rflag = c->d_info + 2 * c->cap_mats;
+    {
+        PhaseScope ps(c, st, PH_MEAN, cur);
+        MeanArgs m;
+        m.theta = d_theta; m.t = c->d_t; m.n = c->N; m.n_pad = c->npad; m.tmean = c->tmean; m.t0 = c->t0;
+        m.y = c->d_y; m.out = c->d_rhs; m.series0 = 0; m.nser = p; m.subtract = 1; m.rflag = d_rflag;
+        mean_kernel<<<dim3(p, Ww), 256, 0, st>>>(c->S, m);
+        LAUNCH_CHECK();
+    }
+    const int small_nb = (c->N + 15) / 16;
+    const bool use_small = !c->no_small && small_nb <= SM_MAXNB;
+    if (use_small) {
+        // K0: assembly + factorisation + solve fused in one CTA's shared memory per (walker, series)
+        PhaseScope ps(c, st, PH_ASM, cur);
+        AsmArgs probe;
+        probe.lower_only = 1; probe.square = 1; probe.add_err = 1; probe.add_jit = 1; probe.pad_identity = 1; probe.vec2 = 1;
+        probe.nser = 1; probe.rows_out = c->npad; probe.cols_out = c->npad; probe.series0 = 0; probe.exact = 0;
+        bool wse = false, fast = true;
+        for (int s = 0; s < p && fast; ++s) {
+            probe.series0 = s;
+            fast = fast_assembly_ok(c, probe, &wse);
+        }
+        SmallArgs sa;
+        sa.theta = d_theta; sa.t = c->d_t; sa.yerr = c->d_yerr; sa.rhs = c->d_rhs; sa.rhs_stride = c->npad;
+        sa.N = c->N; sa.nb = small_nb; sa.fast = (fast && !c->exact) ? 1 : 0; sa.exact = c->exact ? 1 : 0; sa.torigin = c->t0;
+        sa.logdet = c->d_logdet; sa.quad = c->d_quad; sa.info = d_infoflag; sa.kflag = d_kflag;
+        const size_t smem = small_smem_bytes(small_nb, c->q);    // <= 227 KB for nb <= 12, q <= 8 (attribute set at create)
+        small_fused_kernel<<<dim3(p, Ww), 256, smem, st>>>(c->S, sa);
+        LAUNCH_CHECK();
+    } else {
+    {
+        PhaseScope ps(c, st, PH_ASM, cur);
+        AsmArgs a;
+        a.theta = d_theta; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N;
+        a.rows_out = c->npad; a.cols_out = c->npad; a.yerr = c->d_yerr; a.out = c->d_A;
+        a.mat_stride = (long long)(np * np); a.ld = c->npad; a.series0 = 0; a.nser = p;
+        a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1;
+        a.use_trig = 1; a.vec2 = 1; a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
+        if (launch_assemble(c, a, Ww, st)) return 1;
+    }
+    CholArgs g;
+    g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = nmat;
+    g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
+    g.info = d_infoflag;
+    g.A0 = c->d_A; g.mat0 = 0;
+    c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
+    const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
+    if (nsub == 1) {
+        if (run_cholesky(c, g, st, &cur)) return 1;
+    } else {
+        // fork: every sub-stream waits for the assembly, factorises its slice of the matrices
+        // (walker results do not depend on the split), and the caller's stream joins them all
+        CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+        for (int si = 0; si < nsub; ++si) {
+            const int m0 = (int)((long long)nmat * si / nsub), m1 = (int)((long long)nmat * (si + 1) / nsub);
+            CholArgs gs = g;
+            gs.A = g.A + (size_t)m0 * g.mat_stride;
+            gs.Linv = g.Linv + (size_t)m0 * TB * TB;
+            gs.rhs = g.rhs + (size_t)m0 * np;
+            gs.logdet = g.logdet + m0;
+            gs.quad = g.quad + m0;
+            gs.info = g.info + m0;
+            gs.nmat = m1 - m0;
+            gs.mat0 = m0;
+            CUDA_TRY(cudaStreamWaitEvent(c->sub[si], c->ev_fork, 0));
+            if (run_cholesky(c, gs, c->sub[si], nullptr)) return 1;
+            CUDA_TRY(cudaEventRecord(c->ev_join[si], c->sub[si]));
+            CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[si], 0));
+        }
+    }
+    }   // !use_small
+    {
+        PhaseScope ps(c, st, PH_FINAL, cur);
+        finalize_kernel<<<(Ww + 127) / 128, 128, 0, st>>>(Ww, p, half_n_log2pi, c->d_quad, c->d_logdet, d_infoflag,
+                                                         d_kflag, d_rflag, d_out, c->d_status);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// Replay (or capture once) the CUDA graph of one wave.  theta is first copied into the context's own
+// buffer and the results are produced in the context's d_out, so the graph's pointers never change; the
+// caller's stream and the internal graph stream are ordered by two events.
+static int run_wave_graph(agpn_ctx* c, int Ww, const double* theta, int theta_on_device, double* d_out_user,
+                          cudaStream_t st, bool* replayed) {
+    *replayed = false;
+    const int D = c->S.D;
+    const int tma = c->maps_valid ? 1 : 0;
+    agpn_ctx::GraphEntry* hit = nullptr;
+    for (auto& ge : c->graphs)
+        if (ge.Ww == Ww && ge.sv == c->struct_version && ge.wv == c->ws_version && ge.exact == (int)c->exact &&
+            ge.group == c->group && ge.nsub == c->nsub && ge.tma == tma && ge.mc == c->tma_mc)
+            hit = &ge;
+    if (!hit) {
+        // stale entries (other structure / workspace) are dropped; at most a handful of batch sizes are kept
+        for (size_t i = 0; i < c->graphs.size();) {
+            if (c->graphs[i].sv != c->struct_version || c->graphs[i].wv != c->ws_version || c->graphs.size() > 8) {
+                cudaGraphExecDestroy(c->graphs[i].exec);
+                c->graphs.erase(c->graphs.begin() + i);
+            } else ++i;
+        }
+        const long long l0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(c->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;                                  // cannot capture here: the caller falls back to plain launches
+        }
+        size_t cur = 0;
+        const int rc = enqueue_wave(c, Ww, c->d_theta, c->d_out, c->gstream, cur);
+        const cudaError_t ee = cudaStreamEndCapture(c->gstream, &graph);
+        if (rc || ee != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc) return rc;
+            c->use_graph = false;
+            return 0;
+        }
+        agpn_ctx::GraphEntry ge;
+        ge.Ww = Ww; ge.sv = c->struct_version; ge.wv = c->ws_version; ge.exact = c->exact; ge.group = c->group;
+        ge.nsub = c->nsub; ge.tma = tma; ge.mc = c->tma_mc; ge.exec = nullptr; ge.nlaunch = g_launches.load() - l0;
+        g_launches.store(l0);                          // captured, not executed
+        const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            cudaGetLastError();
+            c->use_graph = false;
+            return 0;
+        }
+        c->graphs.push_back(ge);
+        hit = &c->graphs.back();
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_theta, theta, sizeof(double) * (size_t)Ww * D,
+                             theta_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(c->ev_gin, st));
+    CUDA_TRY(cudaStreamWaitEvent(c->gstream, c->ev_gin, 0));
+    CUDA_TRY(cudaGraphLaunch(hit->exec, c->gstream));
+    g_launches.fetch_add(hit->nlaunch);
+    CUDA_TRY(cudaEventRecord(c->ev_gout, c->gstream));
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_gout, 0));
+    if (d_out_user != c->d_out)
+        CUDA_TRY(cudaMemcpyAsync(d_out_user, c->d_out, sizeof(double) * Ww, cudaMemcpyDeviceToDevice, st));
+    *replayed = true;
+    return 0;
+}
+
 extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int theta_on_device,
                                   double* out, int out_on_device, int* status, void* stream) {
     if (!c || !theta || !out) USAGE_FAIL("agpn_loglike_batch: null pointer");
@@ -521,95 +698,20 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
 
     for (size_t w0 = 0; w0 < (size_t)W; w0 += wave) {
         const int Ww = (int)std::min(wave, (size_t)W - w0);
-        const int nmat = Ww * p;
         size_t cur = 0;
-        const double* d_theta = theta + w0 * D;
-        if (!theta_on_device) {
-            CUDA_TRY(cudaMemcpyAsync(c->d_theta, theta + w0 * D, sizeof(double) * Ww * D, cudaMemcpyHostToDevice, st));
-            d_theta = c->d_theta;
-        }
-        CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double) * nmat, st));
-        CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double) * nmat, st));
-        CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 3 * c->cap_mats, st));
-        int* d_infoflag = c->d_info;
-        int* d_kflag = c->d_info + c->cap_mats;
-        int* d_rflag = c->d_info + 2 * c->cap_mats;
-        {
-            PhaseScope ps(c, st, PH_MEAN, cur);
-            MeanArgs m;
-            m.theta = d_theta; m.t = c->d_t; m.n = c->N; m.n_pad = c->npad; m.tmean = c->tmean; m.t0 = c->t0;
-            m.y = c->d_y; m.out = c->d_rhs; m.series0 = 0; m.nser = p; m.subtract = 1; m.rflag = d_rflag;
-            mean_kernel<<<dim3(p, Ww), 256, 0, st>>>(c->S, m);
-            LAUNCH_CHECK();
-        }
-        const int small_nb = (c->N + 15) / 16;
-        const bool use_small = !c->no_small && small_nb <= SM_MAXNB;
-        if (use_small) {
-            // K0: assembly + factorisation + solve fused in one CTA's shared memory per (walker, series)
-            PhaseScope ps(c, st, PH_ASM, cur);
-            AsmArgs probe;
-            probe.lower_only = 1; probe.square = 1; probe.add_err = 1; probe.add_jit = 1; probe.pad_identity = 1; probe.vec2 = 1;
-            probe.nser = 1; probe.rows_out = c->npad; probe.cols_out = c->npad; probe.series0 = 0; probe.exact = 0;
-            bool wse = false, fast = true;
-            for (int s = 0; s < p && fast; ++s) {
-                probe.series0 = s;
-                fast = fast_assembly_ok(c, probe, &wse);
-            }
-            SmallArgs sa;
-            sa.theta = d_theta; sa.t = c->d_t; sa.yerr = c->d_yerr; sa.rhs = c->d_rhs; sa.rhs_stride = c->npad;
-            sa.N = c->N; sa.nb = small_nb; sa.fast = (fast && !c->exact) ? 1 : 0; sa.exact = c->exact ? 1 : 0; sa.torigin = c->t0;
-            sa.logdet = c->d_logdet; sa.quad = c->d_quad; sa.info = d_infoflag; sa.kflag = d_kflag;
-            const size_t smem = small_smem_bytes(small_nb, c->q);    // <= 227 KB for nb <= 12, q <= 8 (attribute set at create)
-            small_fused_kernel<<<dim3(p, Ww), 256, smem, st>>>(c->S, sa);
-            LAUNCH_CHECK();
-        } else {
-        {
-            PhaseScope ps(c, st, PH_ASM, cur);
-            AsmArgs a;
-            a.theta = d_theta; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N;
-            a.rows_out = c->npad; a.cols_out = c->npad; a.yerr = c->d_yerr; a.out = c->d_A;
-            a.mat_stride = (long long)(np * np); a.ld = c->npad; a.series0 = 0; a.nser = p;
-            a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1;
-            a.use_trig = 1; a.vec2 = 1; a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
-            if (launch_assemble(c, a, Ww, st)) return 1;
-        }
-        CholArgs g;
-        g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = nmat;
-        g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
-        g.info = d_infoflag;
-        g.A0 = c->d_A; g.mat0 = 0;
-        c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
-        const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
-        if (nsub == 1) {
-            if (run_cholesky(c, g, st, &cur)) return 1;
-        } else {
-            // fork: every sub-stream waits for the assembly, factorises its slice of the matrices
-            // (walker results do not depend on the split), and the caller's stream joins them all
-            CUDA_TRY(cudaEventRecord(c->ev_fork, st));
-            for (int si = 0; si < nsub; ++si) {
-                const int m0 = (int)((long long)nmat * si / nsub), m1 = (int)((long long)nmat * (si + 1) / nsub);
-                CholArgs gs = g;
-                gs.A = g.A + (size_t)m0 * g.mat_stride;
-                gs.Linv = g.Linv + (size_t)m0 * TB * TB;
-                gs.rhs = g.rhs + (size_t)m0 * np;
-                gs.logdet = g.logdet + m0;
-                gs.quad = g.quad + m0;
-                gs.info = g.info + m0;
-                gs.nmat = m1 - m0;
-                gs.mat0 = m0;
-                CUDA_TRY(cudaStreamWaitEvent(c->sub[si], c->ev_fork, 0));
-                if (run_cholesky(c, gs, c->sub[si], nullptr)) return 1;
-                CUDA_TRY(cudaEventRecord(c->ev_join[si], c->sub[si]));
-                CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[si], 0));
-            }
-        }
-        }   // !use_small
         double* d_out = out_on_device ? out + w0 : c->d_out;
-        {
-            PhaseScope ps(c, st, PH_FINAL, cur);
-            finalize_kernel<<<(Ww + 127) / 128, 128, 0, st>>>(Ww, p, half_n_log2pi, c->d_quad, c->d_logdet, d_infoflag,
-                                                             d_kflag, d_rflag, d_out, c->d_status);
-            LAUNCH_CHECK();
+        bool replayed = false;
+        if (c->use_graph && !c->profiling) {
+            const int grc = run_wave_graph(c, Ww, theta + w0 * D, theta_on_device, d_out, st, &replayed);
+            if (grc) return grc;
+        }
+        if (!replayed) {
+            const double* d_theta = theta + w0 * D;
+            if (!theta_on_device) {
+                CUDA_TRY(cudaMemcpyAsync(c->d_theta, theta + w0 * D, sizeof(double) * Ww * D, cudaMemcpyHostToDevice, st));
+                d_theta = c->d_theta;
+            }
+            if (enqueue_wave(c, Ww, d_theta, d_out, st, cur)) return 1;
         }
         if (!out_on_device)
             CUDA_TRY(cudaMemcpyAsync(out + w0, c->d_out, sizeof(double) * Ww, cudaMemcpyDeviceToHost, st));
