@@ -91,6 +91,7 @@ struct agpn_ctx {
     bool use_tma = false;      // AGPN_SYRK=tma | tma_nomc selects the TMA trailing-update kernel (default: cp.async, faster by 1-4 %)
     bool maps_valid = false;
     int tma_mc = 1;            // multicast the shared A operand inside the CTA pair (AGPN_SYRK=tma_nomc: off)
+    int tma_which = 3;         // bit 0: narrow updates, bit 1: wide updates (AGPN_SYRK=tma_narrow / tma_wide)
     CUtensorMap tmA, tmB;
     int group = 8;             // block columns per wide trailing update (AGPN_GROUP)
     bool group_fixed = false;  // AGPN_GROUP given: no adaptation to the batch size
@@ -205,7 +206,8 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_GROUP")) { c->group = atoi(e) > 0 ? atoi(e) : 8; c->group_fixed = true; }
     if (const char* e = getenv("AGPN_GENERIC_ASM")) c->no_fast_asm = atoi(e) != 0;
     if (const char* e = getenv("AGPN_NO_SMALL")) c->no_small = atoi(e) != 0;
-    if (const char* e = getenv("AGPN_SYRK")) { c->use_tma = strncmp(e, "tma", 3) == 0; c->tma_mc = strcmp(e, "tma_nomc") != 0; }
+    if (const char* e = getenv("AGPN_SYRK")) { c->use_tma = strncmp(e, "tma", 3) == 0; c->tma_mc = strcmp(e, "tma_nomc") != 0;
+        c->tma_which = strcmp(e, "tma_narrow") == 0 ? 1 : (strcmp(e, "tma_wide") == 0 ? 2 : 3); }
     memset(&c->S, 0, sizeof(Structure));
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_t, sizeof(double) * N)) != cudaSuccess ||
@@ -429,7 +431,7 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
         for (int k = k0; k < kend; ++k) {
             if (k > k0) {
                 PhaseScope ps(c, st, PH_SYRK, cur);
-                if (c->maps_valid)
+                if (c->maps_valid && (c->tma_which & 1))
                     syrk_tma_kernel<<<dim3(2 * (g.nblk - k), g.nmat), TMA_THREADS, TMA_SMEM_BYTES, st>>>(c->tmA, c->tmB, g, k0, k - k0, k, 1, c->tma_mc);
                 else
                     syrk_kernel<<<dim3(2 * (g.nblk - k), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
@@ -449,7 +451,7 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
         const int nt = g.nblk - kend;
         if (nt > 0) {
             PhaseScope ps(c, st, PH_SYRK, cur);
-            if (c->maps_valid)
+            if (c->maps_valid && (c->tma_which & 2))
                 syrk_tma_kernel<<<dim3(nt * (nt + 1), g.nmat), TMA_THREADS, TMA_SMEM_BYTES, st>>>(c->tmA, c->tmB, g, k0, kend - k0, kend, 0, c->tma_mc);
             else
                 syrk_kernel<<<dim3(nt * (nt + 1), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
