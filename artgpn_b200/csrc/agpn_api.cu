@@ -17,6 +17,7 @@
 #include "agpn_predict.cuh"
 #include "agpn_small.cuh"
 #include "agpn_tma.cuh"
+#include "agpn_i8.cuh"
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
@@ -45,7 +46,7 @@ static std::atomic<long long> g_launches{0};
         CUDA_TRY(cudaGetLastError());   \
     } while (0)
 
-enum { PH_MEAN = 0, PH_ASM = 1, PH_DIAG = 2, PH_TRSM = 3, PH_SYRK = 4, PH_FINAL = 5, PH_COUNT = 6 };
+enum { PH_MEAN = 0, PH_ASM = 1, PH_DIAG = 2, PH_TRSM = 3, PH_SYRK = 4, PH_FINAL = 5, PH_SLICE = 6, PH_COUNT = 7 };
 
 struct agpn_ctx {
     int device = 0;
@@ -82,8 +83,8 @@ struct agpn_ctx {
     double* d_augv = nullptr;  // rhs of the augmented system | second theta row
     // profiling
     bool profiling = false;
-    double phase_ms[PH_COUNT] = {0, 0, 0, 0, 0, 0};
-    long long phase_launches[PH_COUNT] = {0, 0, 0, 0, 0, 0};
+    double phase_ms[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    long long phase_launches[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
     struct Ev { cudaEvent_t a, b; int ph; };
     std::vector<Ev> evs;
     bool attrs_set = false;
@@ -93,6 +94,11 @@ struct agpn_ctx {
     int tma_mc = 1;            // multicast the shared A operand inside the CTA pair (AGPN_SYRK=tma_nomc: off)
     int tma_which = 3;         // bit 0: narrow updates, bit 1: wide updates (AGPN_SYRK=tma_narrow / tma_wide)
     CUtensorMap tmA, tmB;
+    // INT8-sliced trailing update (agpn_i8.cuh): bit 0 = narrow updates, bit 1 = wide updates (AGPN_SYRK=i8 | i8_narrow | i8_wide)
+    int i8_which = 0;
+    signed char* d_S8 = nullptr;   // [cap_mats] digit planes of one group of block columns
+    double* d_rscale = nullptr;    // [cap_mats][2][npad]
+    int sgroup = 0;                // block columns the slice storage holds per matrix
     int group = 8;             // block columns per wide trailing update (AGPN_GROUP)
     bool group_fixed = false;  // AGPN_GROUP given: no adaptation to the batch size
     int group_eff = 8;         // group used by the current call (set from the TOTAL number of matrices)
@@ -174,6 +180,7 @@ static int set_kernel_attrs(agpn_ctx* c) {
     CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
     // function attributes are per function (not per context): always allow the largest K0 configuration
     {
         cudaFuncAttributes fa;
@@ -208,6 +215,10 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_NO_SMALL")) c->no_small = atoi(e) != 0;
     if (const char* e = getenv("AGPN_SYRK")) { c->use_tma = strncmp(e, "tma", 3) == 0; c->tma_mc = strcmp(e, "tma_nomc") != 0;
         c->tma_which = strcmp(e, "tma_narrow") == 0 ? 1 : (strcmp(e, "tma_wide") == 0 ? 2 : 3); }
+    if (const char* e = getenv("AGPN_SYRK")) {
+        if (strncmp(e, "i8", 2) == 0) c->i8_which = strcmp(e, "i8_narrow") == 0 ? 1 : (strcmp(e, "i8_wide") == 0 ? 2 : 3);
+    }
+    if (c->group > 64) c->group = 64;     // int32 accumulators of the INT8 path: depth <= 256 block columns
     memset(&c->S, 0, sizeof(Structure));
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_t, sizeof(double) * N)) != cudaSuccess ||
@@ -264,6 +275,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_t); cudaFree(c->d_y); cudaFree(c->d_yerr);
     cudaFree(c->d_A); cudaFree(c->d_Linv); cudaFree(c->d_rhs); cudaFree(c->d_logdet); cudaFree(c->d_quad);
     cudaFree(c->d_info); cudaFree(c->d_theta); cudaFree(c->d_out); cudaFree(c->d_status);
+    cudaFree(c->d_S8); cudaFree(c->d_rscale);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
     delete c;
     return 0;
@@ -334,12 +346,21 @@ extern "C" int agpn_set_profiling(agpn_ctx* c, int enable) {
 
 extern "C" int agpn_phase_ms(agpn_ctx* c, double* ms6, long long* launches6) {
     if (!c) USAGE_FAIL("agpn_phase_ms: null context");
-    for (int i = 0; i < PH_COUNT; ++i) {
+    for (int i = 0; i < 6; ++i) {
         if (ms6) ms6[i] = c->phase_ms[i];
         if (launches6) launches6[i] = c->phase_launches[i];
     }
     return 0;
 }
+
+extern "C" int agpn_slice_ms(agpn_ctx* c, double* ms, long long* launches) {
+    if (!c) USAGE_FAIL("agpn_slice_ms: null context");
+    if (ms) *ms = c->phase_ms[PH_SLICE];
+    if (launches) *launches = c->phase_launches[PH_SLICE];
+    return 0;
+}
+
+extern "C" int agpn_update_path(const agpn_ctx* c) { return c ? c->i8_which : -1; }
 
 // ---- profiling helpers ---------------------------------------------------------------------
 struct PhaseScope {
@@ -380,7 +401,9 @@ static void collect_phases(agpn_ctx* c, size_t used) {
 static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
     if (nmat > c->cap_mats) {
         cudaFree(c->d_A); cudaFree(c->d_Linv); cudaFree(c->d_rhs); cudaFree(c->d_logdet); cudaFree(c->d_quad); cudaFree(c->d_info);
-        c->d_A = c->d_Linv = c->d_rhs = c->d_logdet = c->d_quad = nullptr;
+        cudaFree(c->d_S8); cudaFree(c->d_rscale);
+        c->d_A = c->d_Linv = c->d_rhs = c->d_logdet = c->d_quad = c->d_rscale = nullptr;
+        c->d_S8 = nullptr;
         c->d_info = nullptr;
         c->cap_mats = 0;
         const size_t np = (size_t)c->npad;
@@ -392,6 +415,11 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_logdet, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 3 * nmat));
+        if (c->i8_which) {
+            c->sgroup = c->group < 2 ? 2 : c->group;
+            CUDA_TRY(cudaMalloc(&c->d_S8, nmat * i8_slices_per_matrix(c->nblk, c->sgroup)));
+            CUDA_TRY(cudaMalloc(&c->d_rscale, sizeof(double) * nmat * 2 * np));
+        }
         c->cap_mats = nmat;
         ++c->ws_version;
     }
@@ -426,12 +454,15 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
     // kstop < nblk: partial factorisation -- only the first kstop block columns are eliminated; the
     // remaining trailing block then holds the Schur complement (used for the predictive covariance)
     if (kstop < 0 || kstop > g.nblk) kstop = g.nblk;
+    const int i8 = (g.S8 && group <= g.sgroup) ? c->i8_which : 0;
     for (int k0 = 0; k0 < kstop; k0 += group) {
         const int kend = (k0 + group < kstop) ? k0 + group : kstop;
         for (int k = k0; k < kend; ++k) {
             if (k > k0) {
                 PhaseScope ps(c, st, PH_SYRK, cur);
-                if (c->maps_valid && (c->tma_which & 1))
+                if (i8 & 1)
+                    syrk_i8_kernel<<<dim3(2 * (g.nblk - k), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
+                else if (c->maps_valid && (c->tma_which & 1))
                     syrk_tma_kernel<<<dim3(2 * (g.nblk - k), g.nmat), TMA_THREADS, TMA_SMEM_BYTES, st>>>(c->tmA, c->tmB, g, k0, k - k0, k, 1, c->tma_mc);
                 else
                     syrk_kernel<<<dim3(2 * (g.nblk - k), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
@@ -447,11 +478,19 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
                 trsm_kernel<<<dim3(g.nblk - k - 1, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
                 LAUNCH_CHECK();
             }
+            // digit planes of the new panel, if a later update of this group reads them on the INT8 path
+            if (k < g.nblk - 1 && ((((i8 & 1) && k + 1 < kend)) || ((i8 & 2) && kend < g.nblk))) {
+                PhaseScope ps(c, st, PH_SLICE, cur);
+                i8_slice_kernel<<<dim3(g.nblk - k - 1, g.nmat), 256, 0, st>>>(g, k, k0);
+                LAUNCH_CHECK();
+            }
         }
         const int nt = g.nblk - kend;
         if (nt > 0) {
             PhaseScope ps(c, st, PH_SYRK, cur);
-            if (c->maps_valid && (c->tma_which & 2))
+            if (i8 & 2)
+                syrk_i8_kernel<<<dim3(nt * (nt + 1), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
+            else if (c->maps_valid && (c->tma_which & 2))
                 syrk_tma_kernel<<<dim3(nt * (nt + 1), g.nmat), TMA_THREADS, TMA_SMEM_BYTES, st>>>(c->tmA, c->tmB, g, k0, kend - k0, kend, 0, c->tma_mc);
             else
                 syrk_kernel<<<dim3(nt * (nt + 1), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
@@ -568,6 +607,13 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     g.info = d_infoflag;
     g.A0 = c->d_A; g.mat0 = 0;
     c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
+    if (c->i8_which && c->d_S8 && c->nblk > 1) {
+        // row scales r_i = sqrt(K_ii) >= |L_ik| from the assembled diagonal, before the factorisation overwrites it
+        g.S8 = c->d_S8; g.rscale = c->d_rscale; g.sgroup = c->sgroup;
+        PhaseScope ps(c, st, PH_SLICE, cur);
+        i8_rowscale_kernel<<<dim3((c->npad + 255) / 256, nmat), 256, 0, st>>>(g);
+        LAUNCH_CHECK();
+    }
     const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
     if (nsub == 1) {
         if (run_cholesky(c, g, st, &cur)) return 1;
@@ -586,6 +632,10 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             gs.info = g.info + m0;
             gs.nmat = m1 - m0;
             gs.mat0 = m0;
+            if (g.S8) {
+                gs.S8 = g.S8 + (size_t)m0 * i8_slices_per_matrix(g.nblk, g.sgroup);
+                gs.rscale = g.rscale + (size_t)m0 * 2 * np;
+            }
             CUDA_TRY(cudaStreamWaitEvent(c->sub[si], c->ev_fork, 0));
             if (run_cholesky(c, gs, c->sub[si], nullptr)) return 1;
             CUDA_TRY(cudaEventRecord(c->ev_join[si], c->sub[si]));
@@ -685,7 +735,8 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t have = c->cap_mats * np * np * sizeof(double);
-        const size_t per_walker = (size_t)p * (np * np + TB * TB + np) * sizeof(double) + 64;
+        const size_t per_walker = (size_t)p * ((np * np + TB * TB + 3 * np) * sizeof(double) +
+                                               (c->i8_which ? i8_slices_per_matrix(c->nblk, c->group < 2 ? 2 : c->group) : 0)) + 64;
         const size_t fit = (size_t)((free_b + have) * 0.85) / per_walker;
         if (fit < 1) USAGE_FAIL("agpn_loglike_batch: not enough device memory for one walker");
         if (wave > fit) wave = fit;

@@ -51,6 +51,10 @@ struct CholArgs {
     int* info;              // [nmat]  0 ok / 1 not positive definite
     double* A0;             // base of the whole batch allocation the tensor maps describe (TMA path)
     int mat0;               // index of this launch's first matrix inside that allocation
+    // INT8-sliced trailing update (agpn_i8.cuh); S8 == nullptr: not in use
+    double* rscale = nullptr;   // [nmat][2][n_pad]  Q / r_i  |  r_i / (126 2^24)
+    signed char* S8 = nullptr;  // [nmat] digit planes of the current group's block columns
+    int sgroup = 0;             // block columns the slice storage of one matrix holds
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {

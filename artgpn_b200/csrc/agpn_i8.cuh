@@ -1,0 +1,314 @@
+// Trailing update of the blocked Cholesky on the INT8 tensor path (tcgen05.mma.kind::i8, TMEM accumulators):
+// the FP64 rank-k update  C_ij -= sum_k L_ik L_jk  evaluated as exact integer products of 7-bit slices
+// (Ozaki-style error-free splitting) -- several times the DMMA.8x8x4 rate of the FP64 tensor pipe.
+//
+// Numbers.  Row i of L is scaled by r_i >= max_k |L_ik| (r_i = sqrt(K_ii): sum_k L_ik^2 = K_ii) and stored as the
+// integer q_ik = rint(L_ik / r_i * Q), Q = 126 * 2^49, split into 8 signed base-128 digits a_0 .. a_7
+// (q = sum_s a_s 128^(7-s), |a_s| <= 64 for s > 0, |a_0| <= 127): 56 bits below the row scale.  Then
+//     sum_k q_ik q_jk = sum_d 128^(14-d) S_d,     S_d = sum_{s+t=d} sum_k a_s(i,k) a_t(j,k)    (exact in int32),
+// and the diagonals d = 0 .. 7 (36 slice pairs) carry everything above 2^-53 of r_i r_j (the dropped d >= 8 terms
+// are ~2^-53 r_i r_j rms at K = 1024).  One TMEM accumulator (128 lanes x 64 columns of int32) per diagonal: 8 x 64 =
+// all 512 TMEM columns, which fixes the CTA tile at 128 x 64.  Consecutive B slices are consecutive rows of the
+// canonical K-major shared-memory layout, so ONE tcgen05.mma with N = 64 n multiplies A_s with slices t0 .. t0+n-1
+// and accumulates into the n adjacent accumulators s+t0 .. s+t0+n-1: 12 MMAs per 32-byte K step instead of 36.
+// The epilogue folds the 8 integer diagonals into one double (H = S_0..S_3 and Lo = S_4..S_7 are exact in a double,
+// val = H 2^28 + Lo is rounded once) and applies r_i r_j / Q^2.
+//
+// Data movement.  The slicing kernel writes the digits in the tensor core's own operand layout (UMMA canonical
+// K-major, no swizzle: 8-row x 16-byte core matrices, LBO = 128 B, SBO = 256 B), tile by tile:
+//     slices[mat][kc32 = (column - first column of the group) / 32][row tile of 128][slice s][4096 B],
+//     in-tile (r, kb) -> (r/8) 256 + (kb/16) 128 + (r%8) 16 + kb%16
+// (only the CURRENT group's block columns are kept: every update reads columns of the group being eliminated),
+// so a stage is filled by plain 1-D bulk copies (cp.async.bulk, no tensor map): 32 KB of A (all 8 slices of 128
+// rows, contiguous) and 8 x 2 KB of B.  The two CTAs that own the left / right 64 columns of a 128 x 128 tile form a
+// cluster and need the same A: each fetches half of it and multicasts it to both (L2 -> SM bytes per CTA and K step:
+// 32 instead of 48 KB).  3 stages x 48 KB; warp 0 = producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+// (TMEM lane quarter = warp % 4); tcgen05.commit (multicast to both CTAs' `empty` barriers) hands stages back.
+// The C tile travels by bulk copies too: every epilogue thread fetches ITS row (512 contiguous bytes) into a
+// padded shared-memory tile before the main loop starts, folds the eight integer diagonals of that row into it
+// after the last MMA and sends the row back with one bulk store -- no thread-per-row strided global access, no
+// barrier between the epilogue threads, and the C latency hides behind the main loop.
+// Measured building blocks: tools/i8_probe.cu, profiles/r01_i8_probe_*.txt.
+#pragma once
+#include "agpn_chol.cuh"
+#include "agpn_tma.cuh"     // cluster helpers, mbar_expect_tx
+
+#define I8_NSL 8
+#define I8_KB 32                                                 // bytes of K per stage = one kind::i8 K step
+#ifndef I8_STAGES
+#define I8_STAGES 3
+#endif
+#define I8_A_BYTES (TB * I8_KB)                                  // 4096 per slice
+#define I8_B_BYTES (BN * I8_KB)                                  // 2048 per slice
+#define I8_STAGE_BYTES (I8_NSL * (I8_A_BYTES + I8_B_BYTES))      // 49152
+#define I8_CROW_BYTES (BN * 8 + 16)                              // padded C row: 16-byte accesses of a warp, one row per lane, conflict free
+#define I8_SMEM_BYTES (I8_STAGES * I8_STAGE_BYTES + TB * I8_CROW_BYTES + 1024)   // + slack for 1024-byte alignment
+#define I8_THREADS 192
+#define I8_Q (126.0 * 562949953421312.0)                         // 126 * 2^49
+#define I8_QMAX (127ll << 49)
+
+// bytes of slice storage per matrix: (128 sgroup / 32) K chunks x nblk row tiles x 8 slices x 4 KB
+__host__ __device__ __forceinline__ size_t i8_slices_per_matrix(int nblk, int sgroup) { return (size_t)(sgroup * 4) * nblk * I8_NSL * I8_A_BYTES; }
+__device__ __forceinline__ size_t i8_tile_off(int kc32, int rt, int nblk) { return ((size_t)kc32 * nblk + rt) * (I8_NSL * I8_A_BYTES); }
+
+// ---- row scales from the diagonal of the assembled matrix: qmul = Q / r, e = r / (126 2^24) ----------------------
+// grid (n_pad / 256, nmat)
+__global__ void __launch_bounds__(256) i8_rowscale_kernel(CholArgs g) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int n = g.nblk * TB;
+    if (i >= n) return;
+    const double d = g.A[(size_t)blockIdx.y * g.mat_stride + (size_t)i * g.ld + i];
+    // a block that is not positive definite / not finite is flagged by the factorisation; its slices only have to be harmless
+    const double r = (d > 0.0 && d < 1.0e300) ? sqrt(d) * (1.0 + 1.0e-9) : 1.0;
+    double* rs = g.rscale + (size_t)blockIdx.y * 2 * n;
+    rs[i] = I8_Q / r;
+    rs[n + i] = r * (1.0 / (126.0 * 16777216.0));
+}
+
+// ---- slicing of block column k (rows below the diagonal block): L -> 8 int8 digit planes --------------------------
+// (k0 = first block column of k's group)  grid (nblk - k - 1, nmat), 256 threads; a thread task = 16 consecutive columns of one row (one 16-byte chunk per slice)
+__global__ void __launch_bounds__(256) i8_slice_kernel(CholArgs g, int k, int k0) {
+    const int rt = k + 1 + blockIdx.x;
+    const int n = g.nblk * TB;
+    const double* A = g.A + (size_t)blockIdx.y * g.mat_stride;
+    const double* qmul = g.rscale + (size_t)blockIdx.y * 2 * n;
+    signed char* S = g.S8 + (size_t)blockIdx.y * i8_slices_per_matrix(g.nblk, g.sgroup);
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const int id = it * 256 + threadIdx.x;
+        const int r8 = id & 7, ch = (id >> 3) & 7, rg = id >> 6;       // ch: 16-column chunk 0..7 of the block column
+        const int row = rg * 8 + r8;
+        const double f = qmul[rt * TB + row];
+        const double* src = A + (size_t)(rt * TB + row) * g.ld + (size_t)k * TB + ch * 16;
+        unsigned w[I8_NSL][4];
+#pragma unroll
+        for (int s = 0; s < I8_NSL; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[s][j] = 0u;
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2) {
+            const double2 v = *reinterpret_cast<const double2*>(src + 2 * c2);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int c = 2 * c2 + hh;
+                long long q = __double2ll_rn((hh ? v.y : v.x) * f);
+                q = q > I8_QMAX ? I8_QMAX : (q < -I8_QMAX ? -I8_QMAX : q);
+#pragma unroll
+                for (int s = I8_NSL - 1; s >= 1; --s) {
+                    const int dgt = (int)((q + 64) & 127) - 64;
+                    q = (q - dgt) >> 7;
+                    w[s][c >> 2] |= (unsigned)(dgt & 255) << (8 * (c & 3));
+                }
+                w[0][c >> 2] |= (unsigned)((int)q & 255) << (8 * (c & 3));
+            }
+        }
+        const int kc32 = 4 * (k - k0) + (ch >> 1);
+        signed char* dst = S + i8_tile_off(kc32, rt, g.nblk) + (size_t)rg * 256 + (ch & 1) * 128 + r8 * 16;
+#pragma unroll
+        for (int s = 0; s < I8_NSL; ++s)
+            *reinterpret_cast<uint4*>(dst + s * I8_A_BYTES) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    }
+}
+
+// ---- tcgen05 / bulk-copy wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(unsigned dst, const void* src, unsigned bytes, unsigned mbar, unsigned short mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "h"(mask) : "memory");
+}
+// K-major, no swizzle, LBO = 128 B, SBO = 256 B, descriptor version 1 (sm_100)
+__device__ __forceinline__ unsigned long long i8_desc(unsigned saddr) {
+    return (unsigned long long)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_i8(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned acc) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(unsigned mbar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+                 ::"r"(mbar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+// exact int32 -> double on the FP64 add pipe: the bits of 2^52 + 2^31 + v, minus the bias (no I2F)
+__device__ __forceinline__ double i8_i2d(int v) {
+    return __hiloint2double(0x43300000, (int)((unsigned)v ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+// A slice sa times B slices tb .. tb+n-1 of one K step: the schedule that covers the 36 pairs with 12 MMAs
+#define I8_MMA(sa, tb, n, first)                                                                                         \
+    mma_i8(tmem + ((sa) + (tb)) * BN, i8_desc(a0 + (sa) * I8_A_BYTES), i8_desc(b0 + (tb) * I8_B_BYTES),                     \
+           idesc0 | ((unsigned)((BN * (n)) >> 3) << 17), (first) ? accum0 : 1u)
+
+// same launch geometry as syrk_kernel / syrk_tma_kernel:
+//   grid.x = 2 * tiles (cluster = left / right half of one 128 x 128 tile), grid.y = matrices
+//   kfirst = first block column of the update = first block column of the slice storage (the group start)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+syrk_i8_kernel(CholArgs g, int kfirst, int depth, int j0, int narrow) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[2 * I8_STAGES + 2];
+    __shared__ unsigned tmem_base_s;
+    __shared__ double ecol[BN];
+    (void)kfirst;
+
+    const int t = blockIdx.x >> 1;
+    int bi, bj;
+    if (narrow) {
+        bi = t;
+        bj = 0;
+    } else {
+        bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        while (bi * (bi + 1) / 2 > t) --bi;
+        bj = t - bi * (bi + 1) / 2;
+    }
+    const int ti = j0 + bi, tj = j0 + bj;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = cluster_ctarank();
+    const int h = (int)rank;                                        // which 64-column half of the tile
+    const int n = g.nblk * TB;
+    const double* esc = g.rscale + (size_t)blockIdx.y * 2 * n + n;
+
+    const unsigned sraw = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned sbase = (sraw + 1023u) & ~1023u;
+    const unsigned cs = sbase + I8_STAGES * I8_STAGE_BYTES;         // C tile, rows of I8_CROW_BYTES
+    const unsigned full = (unsigned)__cvta_generic_to_shared(bars);
+    const unsigned empty = full + 8 * I8_STAGES, done = full + 16 * I8_STAGES, cfull = done + 8;
+    // right half of a diagonal tile: rows 0..63 lie strictly above the diagonal, never read or written
+    const bool half_tile = (bi == bj && h == 1);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < I8_STAGES; ++s) {
+            mbar_init(full + 8 * s, 1);
+            mbar_init(empty + 8 * s, 2);                            // one tcgen05.commit from each CTA of the pair
+        }
+        mbar_init(done, 1);
+        mbar_init(cfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < BN) ecol[tid] = 0.5 * esc[tj * TB + h * BN + tid];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                             // both CTAs' barriers exist before any multicast / remote commit
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem = tmem_base_s;
+    const int nks = depth * (TB / I8_KB);
+
+    if (warp == 0) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const signed char* S = g.S8 + (size_t)blockIdx.y * i8_slices_per_matrix(g.nblk, g.sgroup);
+            for (int ks = 0; ks < nks; ++ks) {
+                const int s = ks % I8_STAGES, u = ks / I8_STAGES;
+                if (u > 0) mbar_wait(empty + 8 * s, (u - 1) & 1);
+                mbar_expect_tx(full + 8 * s, I8_STAGE_BYTES);
+                const unsigned dst = sbase + s * I8_STAGE_BYTES;
+                // my half of the A stage (slices 4 rank .. 4 rank + 3), delivered to both CTAs
+                bulk_g2s_mc(dst + rank * (4 * I8_A_BYTES), S + i8_tile_off(ks, ti, g.nblk) + rank * (4 * I8_A_BYTES), 4 * I8_A_BYTES,
+                            full + 8 * s, (unsigned short)3);
+                const signed char* bsrc = S + i8_tile_off(ks, tj, g.nblk) + h * I8_B_BYTES;
+#pragma unroll
+                for (int sl = 0; sl < I8_NSL; ++sl)
+                    bulk_g2s(dst + I8_NSL * I8_A_BYTES + sl * I8_B_BYTES, bsrc + sl * I8_A_BYTES, I8_B_BYTES, full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            // kind::i8: D = s32 (2 << 4), A, B = signed 8 bit (1 << 7, 1 << 10), K-major both, M = 128
+            const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TB >> 4) << 24);
+            for (int ks = 0; ks < nks; ++ks) {
+                const int s = ks % I8_STAGES;
+                mbar_wait(full + 8 * s, (ks / I8_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const unsigned a0 = sbase + s * I8_STAGE_BYTES, b0 = a0 + I8_NSL * I8_A_BYTES;
+                const unsigned accum0 = ks > 0 ? 1u : 0u;
+                I8_MMA(0, 0, 4, true);
+                I8_MMA(0, 4, 4, true);
+                I8_MMA(1, 0, 4, false);
+                I8_MMA(1, 4, 3, false);
+                I8_MMA(2, 0, 4, false);
+                I8_MMA(2, 4, 2, false);
+                I8_MMA(3, 0, 4, false);
+                I8_MMA(3, 4, 1, false);
+                I8_MMA(4, 0, 4, false);
+                I8_MMA(5, 0, 3, false);
+                I8_MMA(6, 0, 2, false);
+                I8_MMA(7, 0, 1, false);
+                umma_commit_mc(empty + 8 * s, (unsigned short)3);
+            }
+            umma_commit(done);
+        }
+    } else {
+        // ---------------- epilogue: thread = one row of the tile (TMEM lane) ----------------
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool skip = half_tile && q < 2;                       // warp-uniform
+        double* Crow = g.A + (size_t)blockIdx.y * g.mat_stride + (size_t)(ti * TB + row) * g.ld + (size_t)tj * TB + h * BN;
+        const unsigned crow = cs + row * I8_CROW_BYTES;
+        if (warp == 2 && lane == 0) mbar_expect_tx(cfull, (half_tile ? TB / 2 : TB) * BN * 8);
+        if (!skip) {
+            bulk_g2s(crow, Crow, BN * 8, cfull);
+            const double ei = esc[ti * TB + row];
+            double* cgen = reinterpret_cast<double*>(smem_raw + (crow - sraw));
+            mbar_wait(done, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            mbar_wait(cfull, 0);
+            __syncwarp();
+            const unsigned tlane = tmem + ((unsigned)(q * 32) << 16);
+#pragma unroll 1
+            for (int c8 = 0; c8 < BN / 8; ++c8) {
+                int v[I8_NSL][8];
+#pragma unroll
+                for (int d = 0; d < I8_NSL; ++d) tmem_ld8(tlane + d * BN + c8 * 8, v[d]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j2 = 0; j2 < 8; j2 += 2) {
+                    double2 cc = *reinterpret_cast<double2*>(cgen + c8 * 8 + j2);
+                    double r2[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int j = j2 + u;
+                        double H = i8_i2d(v[0][j]), Lo = i8_i2d(v[4][j]);
+#pragma unroll
+                        for (int d = 1; d < 4; ++d) {
+                            H = fma(H, 128.0, i8_i2d(v[d][j]));
+                            Lo = fma(Lo, 128.0, i8_i2d(v[4 + d][j]));
+                        }
+                        const double val = fma(H, 268435456.0, Lo);      // H 2^28 + Lo = sum_d 128^(7-d) S_d, one rounding
+                        r2[u] = (val * ei) * ecol[c8 * 8 + j];
+                    }
+                    cc.x -= r2[0];
+                    cc.y -= r2[1];
+                    *reinterpret_cast<double2*>(cgen + c8 * 8 + j2) = cc;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            bulk_s2g(Crow, crow, BN * 8);
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();        // nobody leaves while the peer may still multicast into / commit onto this CTA
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}

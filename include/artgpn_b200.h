@@ -181,6 +181,15 @@ long long agpn_launch_count(void);
 int agpn_set_profiling(agpn_ctx* ctx, int enable);
 int agpn_phase_ms(agpn_ctx* ctx, double* ms6, long long* launches6);
 
+/* Trailing-update path of this context (the reference has one path: LAPACK dpotrf inside scipy cho_factor,
+ * arttwo.py:284): 0 = FP64 tensor instruction (DMMA.8x8x4) everywhere; bit 0 / bit 1 set = the narrow / wide
+ * rank-k updates run as exact integer products of 7-bit slices on the INT8 tensor path (tcgen05.mma.kind::i8,
+ * 56 bits below each row's scale -- FP64-equivalent, bit-reproducible).  Chosen at agpn_create from the
+ * environment (AGPN_SYRK = dmma | i8 | i8_wide | i8_narrow).
+ * agpn_slice_ms: device milliseconds / launches of the digit-slicing kernels of the last profiled call. */
+int agpn_update_path(const agpn_ctx* ctx);
+int agpn_slice_ms(agpn_ctx* ctx, double* ms, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,68 @@
+"""INT8-sliced trailing update vs the DMMA path on the same inputs (GPU): log-likelihood agreement and timing.
+usage: python tools/i8_check.py            (contexts read AGPN_SYRK when they are created)"""
+import os
+import sys
+import time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from artgpn_b200 import synth, node, weight, mean
+from artgpn_b200.arttwo import network
+
+
+def make(N, W, mode, q=2, group=None):
+    if mode:
+        os.environ["AGPN_SYRK"] = mode
+    else:
+        os.environ.pop("AGPN_SYRK", None)
+    if group:
+        os.environ["AGPN_GROUP"] = str(group)
+    else:
+        os.environ.pop("AGPN_GROUP", None)
+    t, y, sig = synth.make_data(N, 3, seed=0)
+    theta = synth.make_walkers(W, p=3, q=q, weights="Constant", seed=1)
+    net = network(q, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+    o = synth.objects_from_row(node, weight, mean, theta[0], 3, q, "Constant")
+    net.set_structure(*o[:3])
+    return net, torch.from_numpy(theta).cuda()
+
+
+def timeit(net, th, steps=3):
+    for _ in range(3):
+        out = net.log_likelihood_batch(th)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = net.log_likelihood_batch(th)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+for N, W in ((300, 6), (1000, 6), (2048, 8)):
+    ref_net, th = make(N, W, None)
+    ref = ref_net.log_likelihood_batch(th).cpu().numpy()
+    for mode in ("i8", "i8_wide", "i8_narrow"):
+        for group in (None, 2, 3):
+            net, th2 = make(N, W, mode, group=group)
+            got = net.log_likelihood_batch(th2).cpu().numpy()
+            got2 = net.log_likelihood_batch(th2).cpu().numpy()
+            rel = np.max(np.abs(got - ref) / np.abs(ref))
+            print("N=%d W=%d %s group=%s: max rel diff vs dmma %.3e  bit-reproducible %s  ll[0]=%.15g ref %.15g" % (
+                N, W, mode, group, rel, bool(np.all(got == got2)), got[0], ref[0]), flush=True)
+
+if len(sys.argv) > 1 and sys.argv[1] == "time":
+    N, W = 2048, 128
+    for mode in (None, "i8", "i8_wide"):
+        for group in (8, 4, 2):
+            net, th = make(N, W, mode, group=group)
+            # warm the clocks up
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < 0.5:
+                net.log_likelihood_batch(th)
+                torch.cuda.synchronize()
+            ms = timeit(net, th, steps=8)
+            print("time N=%d W=%d mode=%s group=%d: %.2f ms/step %.1f evals/s" % (N, W, mode, group, ms, W / ms * 1e3), flush=True)
+            del net
+            torch.cuda.empty_cache()
