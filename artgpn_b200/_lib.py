@@ -47,6 +47,8 @@ _SIGNATURES = {
     "agpn_launch_count": (ctypes.c_longlong, []),
     "agpn_set_profiling": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "agpn_phase_ms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
+    "agpn_update_path": (ctypes.c_int, [c_void_p]),
+    "agpn_slice_ms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -446,6 +446,18 @@ class network(object):
         _lib.check(_lib.load().agpn_phase_ms(self._ctx(), _lib.ptr(ms), _lib.ptr(n)))
         return ms, n
 
+    def update_path(self):
+        """0: every trailing update on the FP64 tensor instruction; bit 0 / bit 1: narrow / wide updates on the
+        INT8-sliced path (chosen at construction from AGPN_SYRK)."""
+        return int(_lib.load().agpn_update_path(self._ctx()))
+
+    def slice_times(self):
+        """(ms, launches) of the digit-slicing kernels of the last profiled log_likelihood_batch."""
+        ms = np.zeros(1)
+        n = np.zeros(1, dtype=np.int64)
+        _lib.check(_lib.load().agpn_slice_ms(self._ctx(), _lib.ptr(ms), _lib.ptr(n)))
+        return float(ms[0]), int(n[0])
+
 
 def evaluate_mean(m, t):
     """Value of one mean-function object on the grid t, computed on the GPU."""

@@ -94,8 +94,10 @@ struct agpn_ctx {
     int tma_mc = 1;            // multicast the shared A operand inside the CTA pair (AGPN_SYRK=tma_nomc: off)
     int tma_which = 3;         // bit 0: narrow updates, bit 1: wide updates (AGPN_SYRK=tma_narrow / tma_wide)
     CUtensorMap tmA, tmB;
-    // INT8-sliced trailing update (agpn_i8.cuh): bit 0 = narrow updates, bit 1 = wide updates (AGPN_SYRK=i8 | i8_narrow | i8_wide)
-    int i8_which = 0;
+    // INT8-sliced trailing update (agpn_i8.cuh), the default: bit 0 = narrow updates, bit 1 = wide updates
+    // (AGPN_SYRK = i8 | i8_narrow | i8_wide; dmma | cpasync | tma* select the FP64 tensor instruction everywhere)
+    int i8_which = 3;
+    int i8_group = 8;              // group of the INT8 path: all block columns (pure left-looking) unless AGPN_GROUP is given
     signed char* d_S8 = nullptr;   // [cap_mats] digit planes of one group of block columns
     double* d_rscale = nullptr;    // [cap_mats][2][npad]
     int sgroup = 0;                // block columns the slice storage holds per matrix
@@ -173,6 +175,13 @@ static bool make_batch_map(CUtensorMap* out, double* base, size_t nmat, int n_pa
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int i8_mode_from_env() {
+    const char* e = getenv("AGPN_SYRK");
+    if (!e || !*e) return 3;
+    if (strncmp(e, "i8", 2) == 0) return strcmp(e, "i8_narrow") == 0 ? 1 : (strcmp(e, "i8_wide") == 0 ? 2 : 3);
+    return 0;
+}
+
 static int set_kernel_attrs(agpn_ctx* c) {
     if (c->attrs_set) return 0;
     CUDA_TRY(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -215,10 +224,11 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_NO_SMALL")) c->no_small = atoi(e) != 0;
     if (const char* e = getenv("AGPN_SYRK")) { c->use_tma = strncmp(e, "tma", 3) == 0; c->tma_mc = strcmp(e, "tma_nomc") != 0;
         c->tma_which = strcmp(e, "tma_narrow") == 0 ? 1 : (strcmp(e, "tma_wide") == 0 ? 2 : 3); }
-    if (const char* e = getenv("AGPN_SYRK")) {
-        if (strncmp(e, "i8", 2) == 0) c->i8_which = strcmp(e, "i8_narrow") == 0 ? 1 : (strcmp(e, "i8_wide") == 0 ? 2 : 3);
-    }
-    if (c->group > 64) c->group = 64;     // int32 accumulators of the INT8 path: depth <= 256 block columns
+    c->i8_which = i8_mode_from_env();
+    // the INT8 path is fastest purely left-looking (every C tile is visited once, measured: C3 25.1 ms with one group
+    // of 16 vs 26.0 with groups of 8; C4 213 vs 249 ms); int32 accumulators bound the depth to 256 block columns
+    c->i8_group = c->group_fixed ? c->group : c->nblk;
+    if (c->i8_group > 256) c->i8_group = 256;
     memset(&c->S, 0, sizeof(Structure));
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_t, sizeof(double) * N)) != cudaSuccess ||
@@ -416,7 +426,7 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 3 * nmat));
         if (c->i8_which) {
-            c->sgroup = c->group < 2 ? 2 : c->group;
+            c->sgroup = c->i8_group < 2 ? 2 : c->i8_group;
             CUDA_TRY(cudaMalloc(&c->d_S8, nmat * i8_slices_per_matrix(c->nblk, c->sgroup)));
             CUDA_TRY(cudaMalloc(&c->d_rscale, sizeof(double) * nmat * 2 * np));
         }
@@ -608,6 +618,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     g.A0 = c->d_A; g.mat0 = 0;
     c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
     if (c->i8_which && c->d_S8 && c->nblk > 1) {
+        c->group_eff = c->i8_group;
         // row scales r_i = sqrt(K_ii) >= |L_ik| from the assembled diagonal, before the factorisation overwrites it
         g.S8 = c->d_S8; g.rscale = c->d_rscale; g.sgroup = c->sgroup;
         PhaseScope ps(c, st, PH_SLICE, cur);
@@ -736,7 +747,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t have = c->cap_mats * np * np * sizeof(double);
         const size_t per_walker = (size_t)p * ((np * np + TB * TB + 3 * np) * sizeof(double) +
-                                               (c->i8_which ? i8_slices_per_matrix(c->nblk, c->group < 2 ? 2 : c->group) : 0)) + 64;
+                                               (c->i8_which ? i8_slices_per_matrix(c->nblk, c->i8_group < 2 ? 2 : c->i8_group) : 0)) + 64;
         const size_t fit = (size_t)((free_b + have) * 0.85) / per_walker;
         if (fit < 1) USAGE_FAIL("agpn_loglike_batch: not enough device memory for one walker");
         if (wave > fit) wave = fit;
@@ -1135,9 +1146,28 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     if (const char* e = getenv("AGPN_SYRK")) { tmp.use_tma = strncmp(e, "tma", 3) == 0; tmp.tma_mc = strcmp(e, "tma_nomc") != 0; }
     tmp.maps_valid = tmp.use_tma && make_batch_map(&tmp.tmA, A, nmat, n_pad, n_pad, TB) && make_batch_map(&tmp.tmB, A, nmat, n_pad, n_pad, BN);
     tmp.group_eff = (tmp.group_fixed || (long long)nmat * (n_pad / TB) >= 384) ? tmp.group : 2;
+    tmp.i8_which = i8_mode_from_env();
+    signed char* d_s8 = nullptr;
+    double* d_rs = nullptr;
+    if (tmp.i8_which && g.nblk > 1) {
+        int ig = tmp.group_fixed ? tmp.group : g.nblk;
+        if (ig > 256) ig = 256;
+        g.sgroup = ig < 2 ? 2 : ig;
+        if (cudaMalloc(&d_s8, (size_t)nmat * i8_slices_per_matrix(g.nblk, g.sgroup)) != cudaSuccess ||
+            cudaMalloc(&d_rs, sizeof(double) * (size_t)nmat * 2 * n_pad) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(d_s8); cudaFree(d_rs); cudaFree(d_linv);
+            USAGE_FAIL("agpn_potrf_batched: not enough device memory for the digit planes");
+        }
+        g.S8 = d_s8; g.rscale = d_rs;
+        tmp.group_eff = ig;
+        i8_rowscale_kernel<<<dim3((n_pad + 255) / 256, nmat), 256, 0, st>>>(g);
+    }
     int rc = run_cholesky(&tmp, g, st, nullptr);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(d_linv);
+    cudaFree(d_s8);
+    cudaFree(d_rs);
     if (rc) return rc;
     CUDA_TRY(e);
     return 0;

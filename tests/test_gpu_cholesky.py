@@ -28,11 +28,18 @@ def _spd(rng, nmat, n, cond_jitter):
     return X @ X.transpose(0, 2, 1) + cond_jitter * np.eye(n)
 
 
-@pytest.fixture(params=["cpasync", "tma", "tma_nomc"])
+@pytest.fixture(params=["i8", "i8:2", "i8_wide:3", "i8_narrow:4", "cpasync", "cpasync:2", "tma", "tma_nomc"])
 def syrk_variant(request, monkeypatch):
-    """Trailing-update kernel: cp.async + mbarrier pipeline (default) or the TMA (cp.async.bulk.tensor)
-    producer-warp kernel with / without cluster multicast (AGPN_SYRK, read per call here)."""
-    monkeypatch.setenv("AGPN_SYRK", request.param)
+    """Trailing-update kernel (AGPN_SYRK[:AGPN_GROUP], read per call here): the INT8-sliced tcgen05 kernel
+    (default; left-looking, or with groups so that narrow and wide updates both run on it, or only one of
+    them), the FP64 cp.async + mbarrier DMMA kernel, or the TMA (cp.async.bulk.tensor) producer-warp DMMA
+    kernel with / without cluster multicast."""
+    kind, _, group = request.param.partition(":")
+    monkeypatch.setenv("AGPN_SYRK", kind)
+    if group:
+        monkeypatch.setenv("AGPN_GROUP", group)
+    else:
+        monkeypatch.delenv("AGPN_GROUP", raising=False)
     return request.param
 
 
@@ -52,7 +59,9 @@ def test_potrf_batched_vs_numpy(n, nmat, syrk_variant):
         assert abs(quad[m] - zref @ zref) <= 1e-9 * abs(quad[m])
 
 
-def test_potrf_flags_not_positive_definite_only_where_it_is():
+@pytest.mark.parametrize("mode", ["i8", "dmma"])
+def test_potrf_flags_not_positive_definite_only_where_it_is(mode, monkeypatch):
+    monkeypatch.setenv("AGPN_SYRK", mode)
     rng = np.random.default_rng(0)
     K = _spd(rng, 4, 256, 1.0)
     K[2, 200, 200] = -5.0            # breaks the second diagonal block of matrix 2 only
@@ -63,8 +72,16 @@ def test_potrf_flags_not_positive_definite_only_where_it_is():
         assert np.allclose(np.tril(L[m]), np.linalg.cholesky(K[m]), rtol=1e-9, atol=1e-10)
 
 
-def test_potrf_full_size_residual_2048():
-    """BASELINE size (2048^2): ||L L^T - K|| / ||K|| at round-off, log-det vs numpy."""
+@pytest.mark.parametrize("mode", ["i8", "i8:8", "dmma"])
+def test_potrf_full_size_residual_2048(mode, monkeypatch):
+    """BASELINE size (2048^2): ||L L^T - K|| / ||K|| at round-off, log-det vs numpy -- on the INT8-sliced update
+    (left-looking and in groups of 8) and on the FP64 tensor instruction."""
+    kind, _, group = mode.partition(":")
+    monkeypatch.setenv("AGPN_SYRK", kind)
+    if group:
+        monkeypatch.setenv("AGPN_GROUP", group)
+    else:
+        monkeypatch.delenv("AGPN_GROUP", raising=False)
     rng = np.random.default_rng(1)
     n = 2048
     K = _spd(rng, 2, n, 10.0)
@@ -76,3 +93,32 @@ def test_potrf_full_size_residual_2048():
         assert res < 1e-13, res
         sign, ld = np.linalg.slogdet(K[m])
         assert abs(2 * logdet[m] - ld) <= 1e-10 * abs(ld)
+
+
+def test_i8_update_is_as_accurate_as_the_fp64_instruction(monkeypatch):
+    """The INT8-sliced update carries 56 bits below each row's scale: its factor must be as close to a
+    long-double reference factor as the DMMA path's, on a matrix with widely varying row scales
+    (diag spread 1e-6 .. 1e6) where a per-row scale matters."""
+    rng = np.random.default_rng(7)
+    n = 768
+    X = rng.normal(size=(n, n // 2))
+    K0 = X @ X.T + 0.05 * n * np.eye(n)
+    d = 10.0 ** rng.uniform(-3, 3, size=n)
+    K = (K0 * d[:, None]) * d[None, :]
+    Kl = K.astype(np.longdouble)
+    # long-double Cholesky (column by column)
+    Lr = np.zeros_like(Kl)
+    for j in range(n):
+        v = Kl[j:, j] - Lr[j:, :j] @ Lr[j, :j]
+        Lr[j:, j] = v / np.sqrt(v[0])
+    Lr = Lr.astype(np.float64)
+    errs = {}
+    for mode in ("i8", "dmma"):
+        monkeypatch.setenv("AGPN_SYRK", mode)
+        monkeypatch.delenv("AGPN_GROUP", raising=False)
+        L, z, logdet, quad, info = _run(K[None].copy(), np.zeros((1, n)))
+        assert info[0] == 0
+        scale = np.sqrt(np.diag(K))[:, None]          # |L_ik| <= sqrt(K_ii): row-relative error
+        errs[mode] = np.max(np.abs(np.tril(L[0]) - Lr) / scale)
+    assert errs["i8"] < 1e-11 and errs["dmma"] < 1e-11, errs
+    assert errs["i8"] <= 4.0 * errs["dmma"] + 1e-15, errs

@@ -80,3 +80,35 @@ def test_ragged_3000_points_three_groups_vs_oracle():
     for w in range(2):
         exp = oracle.log_likelihood(t, y, sig, 2, *synth.objects_from_row(m, m, m, theta[w], 2, 2, "SquaredExponential"))
         assert abs(got[w] - exp) <= 1e-9 * abs(exp), (w, got[w], exp)
+
+
+def test_c3_update_paths_agree_and_match_oracle(monkeypatch):
+    """BASELINE size: INT8-sliced update (default left-looking, groups of 4 with wide updates) and the FP64
+    tensor instruction give the same log-likelihoods to round-off, each within 1e-9 of the oracle."""
+    from artgpn_b200 import synth, node, weight, mean
+    from artgpn_b200.arttwo import network
+    t, y, sig = synth.make_data(2048, 3, seed=0)
+    theta = synth.make_walkers(3, p=3, q=2, weights="Constant", seed=1)
+
+    class M(object):
+        def __getattr__(self, name):
+            return lambda *pars: (name, list(pars))
+    m = M()
+    exp = oracle.log_likelihood(t, y, sig, 2, *synth.objects_from_row(m, m, m, theta[2], 3, 2, "Constant"))
+    got = {}
+    for mode, group, path in (("i8", None, 3), ("i8", "4", 3), ("i8_wide", "4", 2), ("dmma", None, 0)):
+        monkeypatch.setenv("AGPN_SYRK", mode)
+        if group:
+            monkeypatch.setenv("AGPN_GROUP", group)
+        else:
+            monkeypatch.delenv("AGPN_GROUP", raising=False)
+        net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+        net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], 3, 2, "Constant")[:3])
+        assert net.update_path() == path
+        got[(mode, group)] = net.log_likelihood_batch(theta)
+        assert np.array_equal(net.log_likelihood_batch(theta), got[(mode, group)])
+        net.close()
+    ref = got[("dmma", None)]
+    for k, v in got.items():
+        assert abs(v[2] - exp) <= 1e-9 * abs(exp), (k, v[2], exp)
+        assert H.rel_err(v, ref) <= 1e-12, (k, v, ref)

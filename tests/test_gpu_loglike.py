@@ -10,14 +10,24 @@ pytestmark = pytest.mark.gpu
 LL_RTOL = 1e-9
 
 
-@pytest.fixture(params=["fused_small", "tiled"])
+@pytest.fixture(params=["fused_small", "tiled", "tiled_dmma", "tiled_i8_groups"])
 def path(request, monkeypatch):
     """N <= 192 normally takes the fused single-CTA kernel (K0); AGPN_NO_SMALL=1 (read when the context
-    is created) forces the tiled assembly + blocked Cholesky path so both are checked on every case."""
-    if request.param == "tiled":
-        monkeypatch.setenv("AGPN_NO_SMALL", "1")
-    else:
+    is created) forces the tiled assembly + blocked Cholesky path so both are checked on every case.
+    The tiled path's trailing update runs on the INT8-sliced tensor path by default (left-looking);
+    `tiled_dmma` selects the FP64 tensor instruction, `tiled_i8_groups` the INT8 path with groups of 2
+    block columns (narrow AND wide INT8 updates)."""
+    monkeypatch.delenv("AGPN_SYRK", raising=False)
+    monkeypatch.delenv("AGPN_GROUP", raising=False)
+    if request.param == "fused_small":
         monkeypatch.delenv("AGPN_NO_SMALL", raising=False)
+    else:
+        monkeypatch.setenv("AGPN_NO_SMALL", "1")
+        if request.param == "tiled_dmma":
+            monkeypatch.setenv("AGPN_SYRK", "dmma")
+        elif request.param == "tiled_i8_groups":
+            monkeypatch.setenv("AGPN_SYRK", "i8")
+            monkeypatch.setenv("AGPN_GROUP", "2")
     return request.param
 
 

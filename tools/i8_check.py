@@ -66,3 +66,21 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
             print("time N=%d W=%d mode=%s group=%d: %.2f ms/step %.1f evals/s" % (N, W, mode, group, ms, W / ms * 1e3), flush=True)
             del net
             torch.cuda.empty_cache()
+
+if len(sys.argv) > 1 and sys.argv[1] == "prof":
+    N, W = 2048, 128
+    for mode, group in ((None, 8), ("i8", 8), ("i8", 16), ("i8", 4), ("i8_wide", 4)):
+        net, th = make(N, W, mode, group=group)
+        for _ in range(3):
+            net.log_likelihood_batch(th)
+        torch.cuda.synchronize()
+        net.set_profiling(True)
+        net.log_likelihood_batch(th)
+        ms, n = net.phase_times()
+        sm, sn = net.slice_times()
+        net.set_profiling(False)
+        ms_step = timeit(net, th, steps=8)
+        print("prof mode=%s group=%d: step %.2f ms | mean %.2f asm %.2f diag %.2f trsm %.2f syrk %.2f final %.2f slice %.2f (launches %s, slice %d)" % (
+            mode, group, ms_step, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], sm, n.tolist(), sn), flush=True)
+        del net
+        torch.cuda.empty_cache()
