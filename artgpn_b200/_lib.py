@@ -44,6 +44,7 @@ _SIGNATURES = {
     "agpn_potrf_batched": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
     "agpn_dmma_peak": (ctypes.c_int, [ctypes.c_int, c_void_p]),
+    "agpn_i8_peak": (ctypes.c_int, [ctypes.c_int, c_void_p]),
     "agpn_launch_count": (ctypes.c_longlong, []),
     "agpn_set_profiling": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "agpn_phase_ms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),

@@ -1173,6 +1173,36 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     return 0;
 }
 
+// ---- INT8 tensor-path peak probe (roofline denominator of syrk_i8_kernel) --------------------
+extern "C" int agpn_i8_peak(int device, double* tops) {
+    if (!tops) USAGE_FAIL("agpn_i8_peak: null pointer");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount, iters = 40000;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    i8_peak_kernel<<<grid, 128>>>(2000, nullptr);
+    LAUNCH_CHECK();
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        i8_peak_kernel<<<grid, 128>>>(iters, nullptr);
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double t = 2.0 * 128.0 * 256.0 * 32.0 * (double)iters * grid / (ms * 1e-3) / 1e12;
+        if (t > best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tops = best;
+    return 0;
+}
+
 // ---- FP64 tensor-pipe peak probe (roofline denominator measured in the same run) -------------
 template <int NACC>
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {

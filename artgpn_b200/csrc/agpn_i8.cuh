@@ -139,6 +139,16 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, int (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
 }
+// wait for a barrier that completes only after milliseconds of tensor work (the trap of mbar_wait is for protocol bugs)
+__device__ __forceinline__ void mbar_wait_long(unsigned addr, unsigned parity) {
+    unsigned done = 0;
+    unsigned long long spins = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && ++spins > (1ull << 32)) __trap();
+    }
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
@@ -311,4 +321,45 @@ syrk_i8_kernel(CholArgs g, int kfirst, int depth, int j0, int narrow) {
     __syncthreads();
     cluster_sync_all();        // nobody leaves while the peer may still multicast into / commit onto this CTA
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+// ---- INT8 tensor-path issue peak (roofline denominator measured in the same run, like dmma_peak_kernel) ------------
+// one CTA per SM; operands resident in shared memory (zeros), M = 128, N = 256, K = 32 kind::i8 MMAs back to back
+// into the two halves of the 512 TMEM columns
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int* sink) {
+    __shared__ __align__(1024) unsigned char ops[TB * I8_KB + 256 * I8_KB];      // A 4 KB | B 8 KB
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (int)sizeof(ops) / 4; i += blockDim.x) reinterpret_cast<unsigned*>(ops)[i] = 0x01010101u;
+    const unsigned done = (unsigned)__cvta_generic_to_shared(&bar);
+    if (tid == 0) {
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem = tmem_base_s;
+    if (tid == 0) {
+        const unsigned a0 = (unsigned)__cvta_generic_to_shared(ops), b0 = a0 + TB * I8_KB;
+        const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(256 >> 3) << 17) | ((unsigned)(TB >> 4) << 24);
+        const unsigned long long ad = i8_desc(a0), bd = i8_desc(b0);
+        for (int it = 0; it < iters; ++it) mma_i8(tmem + (it & 1) * 256, ad, bd, idesc, it > 1 ? 1u : 0u);
+        umma_commit(done);
+    }
+    mbar_wait_long(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    int v[8];
+    tmem_ld8(tmem + ((unsigned)(warp * 32) << 16), v);
+    tmem_ld_wait();
+    if (sink && v[0] == -12345) sink[blockIdx.x * blockDim.x + tid] = v[1];     // keeps the accumulators observable
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }

@@ -14,9 +14,14 @@ walkers in total.  Rank 0 prints ONE JSON line.
 `value`  : evals/s, theta already resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : evals/s through network.log_likelihood_batch(host numpy theta) -- H2D of theta and
            D2H of the results inside the timed region.
-`roofline`: the batched Cholesky (diagonal-block + panel-solve + trailing-update kernels) against
-           the FP64 tensor (DMMA.8x8x4) issue peak measured in this run; `roofline_assembly`
-           is the covariance assembly kernel against the measured HBM bandwidth.
+`roofline`: the dominant kernel -- the trailing update.  Default path: syrk_i8_kernel, exact integer products
+           of 7-bit slices on the INT8 tensor path (tcgen05.mma.kind::i8), executed INT8 ops against the
+           kind::i8 issue peak measured in this run (agpn_i8_peak); with AGPN_SYRK=dmma: syrk_kernel against the
+           FP64 tensor (DMMA.8x8x4) issue peak measured in this run.
+`roofline_cholesky`: the whole batched Cholesky (diagonal-block + panel-solve + digit-slicing + trailing-update
+           kernels), ALGORITHMIC FP64 flops p N^3 / 3 per eval against the DMMA.8x8x4 peak (BASELINE's
+           "% FP64 TC peak"; above 1.0 on the INT8-sliced path).  `roofline_assembly`: the covariance
+           assembly kernel against the measured HBM bandwidth.
 `cpu_baseline`: the oracle port of the reference (numpy + scipy LAPACK) on the host cores, a bounded
            sample of the same walkers, reference-style process pool with 1 BLAS thread each.
 """
@@ -291,14 +296,19 @@ def main():
     net.set_profiling(True)
     phase = np.zeros(6)
     nl = np.zeros(6, dtype=np.int64)
+    slice_ms, slice_n = 0.0, 0
     PROF_STEPS = 2
     for _ in range(PROF_STEPS):
         net.log_likelihood_batch(theta_d)
         msv, nv = net.phase_times()
         phase += msv
         nl = nv
+        sm_, slice_n = net.slice_times()
+        slice_ms += sm_
     phase /= PROF_STEPS
+    slice_ms /= PROF_STEPS
     net.set_profiling(False)
+    update_path = net.update_path()
 
     if rank == 0:
         peak_tf = np.zeros(1)
@@ -306,22 +316,57 @@ def main():
         peaks, peak_src = load_peaks()
         p, N = cfg["p"], cfg["N"]
         chol_flops = W_local * p * N ** 3 / 3.0                   # F_chol = p N^3 / 3 per eval
-        chol_ms = float(phase[2] + phase[3] + phase[4])
+        chol_ms = float(phase[2] + phase[3] + phase[4] + slice_ms)
+        step_prof_ms = float(phase.sum() + slice_ms)
         chol_tf = chol_flops / (chol_ms * 1e-3) / 1e12
         nblk = (N + 127) // 128
         syrk_tiles = sum((nblk - k - 1) * (nblk - k) // 2 for k in range(nblk))
         syrk_tf = W_local * p * syrk_tiles * 2.0 * 128 ** 3 / (phase[4] * 1e-3) / 1e12 if phase[4] > 0 else None
         asm_bytes = W_local * 4.0 * p * N * (N + 1)               # triangle-only store: B_tri = 4 p N (N+1)
         asm_gbs = asm_bytes / (phase[1] * 1e-3) / 1e9
-        chol_traffic = asm_traffic = None                         # DRAM bytes from the committed ncu pass
+        chol_traffic = asm_traffic = syrk_traffic = None          # DRAM bytes from the committed ncu pass
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tr = json.load(f)
-            if tr.get("workload") == args.workload and args.weights == "Constant":
+            if tr.get("workload") == args.workload and args.weights == "Constant" and tr.get("update_path") == update_path:
                 chol_traffic = tr["cholesky_dram_bytes_per_step"] * W_local / tr["walkers"]
                 asm_traffic = tr["assembly_dram_bytes_per_launch"] * W_local / tr["walkers"]
+                syrk_traffic = tr["syrk_dram_bytes_per_step"] * W_local / tr["walkers"]
         except Exception:
             pass
+        dmma_peak = float(peak_tf[0])
+        syrk_share = float(phase[4] / max(step_prof_ms, 1e-9))
+        if update_path:
+            i8_peak = np.zeros(1)
+            _lib.check(lib.agpn_i8_peak(local_rank, _lib.ptr(i8_peak)))
+            i8_peak = float(i8_peak[0])
+            # 36 slice pairs (s + t <= 7) per FP64 product, 2 ops per int8 multiply-add
+            syrk_tops = 36.0 * syrk_tf if syrk_tf else None
+            roofline = {
+                "bound": "tensor",
+                "kernel": "syrk_i8_kernel: trailing update as exact integer products of 8 x 7-bit slices, "
+                          "tcgen05.mma.kind::i8 with TMEM int32 accumulators (all launches of a step)",
+                "achieved": syrk_tops, "peak": i8_peak, "unit": "TOP/s",
+                "frac": (syrk_tops / i8_peak) if syrk_tops else None,
+                "peak_source": "kind::i8 issue peak (M=128, N=256, operands resident in shared memory) measured in this run "
+                               "(agpn_i8_peak); MEASURED_PEAKS.json has no INT8 figure (2 x its bf16 burst = %.0f TOP/s)"
+                               % (2.0 * peaks.get("bf16_tflops", float("nan"))),
+                "ops_per_step": (36.0 * W_local * p * syrk_tiles * 2.0 * 128 ** 3),
+                "ms": float(phase[4]), "launches": int(nl[4]), "share_of_step_ms": syrk_share,
+                "traffic": syrk_traffic,
+                "traffic_note": "DRAM bytes of all syrk_i8_kernel launches of one step, ncu pass in profiles/ (scaled by walkers)",
+                "fp64_equivalent": {"tflops": syrk_tf, "dmma_peak_tflops": dmma_peak,
+                                    "ratio_to_dmma_peak": (syrk_tf / dmma_peak) if syrk_tf else None,
+                                    "note": "the same update on the FP64 tensor instruction cannot exceed 1.0"},
+                "note": "executed ops (full diagonal tiles counted), CUDA-event time of the launches in a profiled pass"}
+        else:
+            roofline = {
+                "bound": "tensor", "kernel": "syrk_kernel (DMMA.8x8x4; all narrow + wide launches of a step)",
+                "achieved": syrk_tf, "peak": dmma_peak, "unit": "TFLOP/s",
+                "frac": (syrk_tf / dmma_peak) if syrk_tf else None,
+                "peak_source": "DMMA.8x8x4 issue peak measured in this run (agpn_dmma_peak); MEASURED_PEAKS.json has no FP64 figure",
+                "ms": float(phase[4]), "launches": int(nl[4]), "share_of_step_ms": syrk_share, "traffic": syrk_traffic,
+                "note": "flops actually executed by the tile GEMMs (full diagonal tiles counted), CUDA-event time of the syrk launches"}
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -336,27 +381,25 @@ def main():
                     "d2h_bytes_per_step": int(W_local * 12)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "batched Cholesky = potrf_diag + trsm + syrk kernels",
-                         "achieved": chol_tf, "peak": float(peak_tf[0]), "unit": "TFLOP/s",
-                         "frac": chol_tf / float(peak_tf[0]),
-                         "peak_source": "DMMA.8x8x4 issue peak measured in this run (agpn_dmma_peak); "
-                                        "MEASURED_PEAKS.json has no FP64 figure",
-                         "flops_per_launch_group": chol_flops, "ms": chol_ms, "traffic": chol_traffic,
-                         "traffic_note": "DRAM bytes of all Cholesky launches of one step, ncu pass in profiles/ (scaled by walkers)",
-                         "syrk_only_tflops": syrk_tf,
-                         "dominant_kernel": {"kernel": "syrk_kernel (all narrow + wide launches of a step)",
-                                             "executed_tflops": syrk_tf,
-                                             "frac": (syrk_tf / float(peak_tf[0])) if syrk_tf else None,
-                                             "share_of_step_ms": float(phase[4] / max(phase.sum(), 1e-9)),
-                                             "note": "flops actually executed by the tile GEMMs (full diagonal tiles "
-                                                     "counted), CUDA-event time of the syrk launches"}},
+            "roofline": roofline,
+            "roofline_cholesky": {"bound": "tensor",
+                                  "kernel": "batched Cholesky = potrf_diag + trsm + digit slicing + trailing-update kernels",
+                                  "achieved": chol_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": chol_tf / dmma_peak,
+                                  "peak_source": "DMMA.8x8x4 issue peak measured in this run (agpn_dmma_peak); "
+                                                 "MEASURED_PEAKS.json has no FP64 figure",
+                                  "flops_per_step": chol_flops, "ms": chol_ms, "traffic": chol_traffic,
+                                  "traffic_note": "DRAM bytes of all Cholesky launches of one step, ncu pass in profiles/ (scaled by walkers)",
+                                  "note": "ALGORITHMIC FP64 flops p N^3 / 3 per eval (SURVEY 8(d)) over the device time of all "
+                                          "factorisation kernels; a fraction above 1.0 means faster than the FP64 tensor "
+                                          "instruction can go: the trailing update runs FP64-equivalent on the INT8 tensor path"},
+            "update_path": {0: "dmma", 1: "i8 narrow", 2: "i8 wide", 3: "i8"}.get(update_path, str(update_path)),
             "roofline_assembly": {"bound": "hbm", "kernel": "assemble_fast_kernel (lower block triangle only; generic assemble_kernel for other kernel classes)",
                                   "achieved": asm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                   "frac": asm_gbs / peaks.get("hbm_gbs"), "peak_source": peak_src,
                                   "bytes_per_launch": asm_bytes, "ms": float(phase[1]), "traffic": asm_traffic},
             "phase_ms": {"mean_residual": float(phase[0]), "assembly": float(phase[1]), "potrf_diag": float(phase[2]),
                          "trsm": float(phase[3]), "syrk": float(phase[4]), "finalize": float(phase[5]),
-                         "launches": [int(x) for x in nl]},
+                         "digit_slicing": float(slice_ms), "launches": [int(x) for x in nl] + [int(slice_n)]},
         }
         if cpu_base is not None:
             ref_vals = np.array(cpu_base.pop("_vals"))

@@ -171,6 +171,11 @@ int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, double* rhs,
  * the denominator bench.py uses for the Cholesky roofline (MEASURED_PEAKS.json has no FP64 figure). */
 int agpn_dmma_peak(int device, double* tflops);
 
+/* Measured issue-rate peak of the INT8 tensor instruction (tcgen05.mma.kind::i8, M = 128, N = 256, operands resident
+ * in shared memory) on `device`, in TOP/s: the denominator bench.py uses for the INT8-sliced trailing update
+ * (MEASURED_PEAKS.json has no INT8 figure). */
+int agpn_i8_peak(int device, double* tops);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 long long agpn_launch_count(void);
 
