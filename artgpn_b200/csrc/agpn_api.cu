@@ -97,6 +97,7 @@ struct agpn_ctx {
     // INT8-sliced trailing update (agpn_i8.cuh), the default: bit 0 = narrow updates, bit 1 = wide updates
     // (AGPN_SYRK = i8 | i8_narrow | i8_wide; dmma | cpasync | tma* select the FP64 tensor instruction everywhere)
     int i8_which = 3;
+    bool fuse_slices = true;       // AGPN_I8_FUSE=0: separate i8_slice_kernel after every panel solve
     int i8_group = 8;              // group of the INT8 path: all block columns (pure left-looking) unless AGPN_GROUP is given
     signed char* d_S8 = nullptr;   // [cap_mats] digit planes of one group of block columns
     double* d_rscale = nullptr;    // [cap_mats][2][npad]
@@ -225,6 +226,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_SYRK")) { c->use_tma = strncmp(e, "tma", 3) == 0; c->tma_mc = strcmp(e, "tma_nomc") != 0;
         c->tma_which = strcmp(e, "tma_narrow") == 0 ? 1 : (strcmp(e, "tma_wide") == 0 ? 2 : 3); }
     c->i8_which = i8_mode_from_env();
+    if (const char* e = getenv("AGPN_I8_FUSE")) c->fuse_slices = atoi(e) != 0;
     // the INT8 path is fastest purely left-looking (every C tile is visited once, measured: C3 25.1 ms with one group
     // of 16 vs 26.0 with groups of 8; C4 213 vs 249 ms); int32 accumulators bound the depth to 256 block columns
     c->i8_group = c->group_fixed ? c->group : c->nblk;
@@ -483,13 +485,17 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
                 potrf_diag_kernel<<<g.nmat, 256, POTRF_SMEM_BYTES, st>>>(g, k);
                 LAUNCH_CHECK();
             }
+            const bool need_slices = k < g.nblk - 1 && ((((i8 & 1) && k + 1 < kend)) || ((i8 & 2) && kend < g.nblk));
+            // the panel solve writes the digit planes itself; the FP64 panel is stored only if somebody reads it
+            // (a DMMA update of a mixed mode, or a caller that wants the factor: g.keep_factor)
+            const int tflags = (need_slices && c->fuse_slices) ? (1 | ((i8 == 3 && !g.keep_factor) ? 2 : 0)) : 0;
             if (k < g.nblk - 1) {
                 PhaseScope ps(c, st, PH_TRSM, cur);
-                trsm_kernel<<<dim3(g.nblk - k - 1, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k);
+                trsm_kernel<<<dim3(g.nblk - k - 1, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k, k0, tflags);
                 LAUNCH_CHECK();
             }
             // digit planes of the new panel, if a later update of this group reads them on the INT8 path
-            if (k < g.nblk - 1 && ((((i8 & 1) && k + 1 < kend)) || ((i8 & 2) && kend < g.nblk))) {
+            if (need_slices && !c->fuse_slices) {
                 PhaseScope ps(c, st, PH_SLICE, cur);
                 i8_slice_kernel<<<dim3(g.nblk - k - 1, g.nmat), 256, 0, st>>>(g, k, k0);
                 LAUNCH_CHECK();
@@ -1147,6 +1153,8 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     tmp.maps_valid = tmp.use_tma && make_batch_map(&tmp.tmA, A, nmat, n_pad, n_pad, TB) && make_batch_map(&tmp.tmB, A, nmat, n_pad, n_pad, BN);
     tmp.group_eff = (tmp.group_fixed || (long long)nmat * (n_pad / TB) >= 384) ? tmp.group : 2;
     tmp.i8_which = i8_mode_from_env();
+    if (const char* e = getenv("AGPN_I8_FUSE")) tmp.fuse_slices = atoi(e) != 0;
+    g.keep_factor = 1;                                   // the caller reads L
     signed char* d_s8 = nullptr;
     double* d_rs = nullptr;
     if (tmp.i8_which && g.nblk > 1) {

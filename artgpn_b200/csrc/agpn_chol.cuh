@@ -55,12 +55,41 @@ struct CholArgs {
     double* rscale = nullptr;   // [nmat][2][n_pad]  Q / r_i  |  r_i / (126 2^24)
     signed char* S8 = nullptr;  // [nmat] digit planes of the current group's block columns
     int sgroup = 0;             // block columns the slice storage of one matrix holds
+    int keep_factor = 0;        // 1: the FP64 panels of L are stored even when only the digit planes are read again
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+
+// ---- digit planes of the INT8-sliced trailing update (agpn_i8.cuh) ---------------------------------------------
+// x = L_ik * Q / r_i, |x| <= 127 * 2^49.  q = rint(x) = sum_s a_s 128^(7-s) with balanced digits a_1 .. a_7 in
+// [-64, 63] and a_0 = the signed rest: adding 64 * (128^0 + .. + 128^6) turns the balanced digits into plain 7-bit
+// fields u = a + 64.  Returns the eight digits of two values as eight 16-bit pieces (value 0 in the low byte).
+#define I8_NSL 8
+#define I8_Q (126.0 * 562949953421312.0)                         // 126 * 2^49
+#define I8_QMAXF (127.0 * 562949953421312.0)
+#define I8_DIGIT_BIAS 0x0001020408102040ll                       // 64 * sum_{j<7} 128^j
+#define I8_TILE_BYTES (I8_NSL * TB * 32)                         // digit planes of 128 rows x 32 columns: 32 KB
+__device__ __forceinline__ void i8_digits2(double x0, double x1, unsigned (&piece)[I8_NSL]) {
+    x0 = fmin(fmax(x0, -I8_QMAXF), I8_QMAXF);                    // NaN -> -QMAX: harmless, the block is flagged elsewhere
+    x1 = fmin(fmax(x1, -I8_QMAXF), I8_QMAXF);
+    const long long q0 = __double2ll_rn(x0) + I8_DIGIT_BIAS, q1 = __double2ll_rn(x1) + I8_DIGIT_BIAS;
+    const unsigned l0 = (unsigned)q0, l1 = (unsigned)q1;
+    const unsigned h0 = (unsigned)(q0 >> 28), h1 = (unsigned)(q1 >> 28);      // digits 4 .. 7 (bits 28 .. 56 + sign)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // slice 7 - j holds digit j (weight 128^j)
+        piece[7 - j] = ((((l0 >> (7 * j)) & 127u) + 192u) & 255u) | (((((l1 >> (7 * j)) & 127u) + 192u) & 255u) << 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        piece[3 - j] = ((((h0 >> (7 * j)) & 127u) + 192u) & 255u) | (((((h1 >> (7 * j)) & 127u) + 192u) & 255u) << 8);
+    piece[0] = ((unsigned)((int)h0 >> 21) & 255u) | (((unsigned)((int)h1 >> 21) & 255u) << 8);
+}
+__host__ __device__ __forceinline__ size_t i8_slices_per_matrix(int nblk, int sgroup) { return (size_t)(sgroup * 4) * nblk * I8_TILE_BYTES; }
+__host__ __device__ __forceinline__ size_t i8_tile_off(int kc32, int rt, int nblk) { return ((size_t)kc32 * nblk + rt) * I8_TILE_BYTES; }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -319,7 +348,11 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
 // half goes first (it reads all 128 input columns), the left half needs only K = 64 because the
 // inverse is lower triangular -- this also makes the in-place overwrite race free.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k) {
+// flags bit 0: also write the digit planes of the new panel (INT8-sliced update; k0 = first block column of the slice
+// storage's group) -- digits are staged in the idle pipeline buffers in the tensor core's operand layout and leave
+// as two contiguous 32 KB blocks per half;  bit 1: do not store the FP64 panel (nothing reads it when every later
+// update runs on the digit planes).
+__global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0, int flags) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double zs[TB];
     __shared__ double red[2][TB];
@@ -354,12 +387,40 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k) {
             for (int ni = 0; ni < 4; ++ni) {
                 const int row = wm * 32 + mi * 8 + (lane >> 2);
                 const int col = h * BN + wn * 32 + ni * 8 + 2 * (lane & 3);
-                *reinterpret_cast<double2*>(Aik + (size_t)row * ld + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                if (!(flags & 2)) *reinterpret_cast<double2*>(Aik + (size_t)row * ld + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
                 if (rhs != nullptr) {
                     part[mi] = fma(acc[mi][ni][0], zs[col], part[mi]);
                     part[mi] = fma(acc[mi][ni][1], zs[col + 1], part[mi]);
                 }
             }
+        if (flags & 1) {
+            __syncthreads();                                       // slower warps may still read the last operand stages
+            unsigned char* stg = reinterpret_cast<unsigned char*>(smem);      // [wn = 32-column chunk][slice][4096]
+            const double* qmul = g.rscale + (size_t)mat * 2 * ((size_t)g.nblk * TB) + (size_t)ti * TB;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const double f = qmul[wm * 32 + mi * 8 + (lane >> 2)];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    unsigned piece[I8_NSL];
+                    i8_digits2(acc[mi][ni][0] * f, acc[mi][ni][1] * f, piece);
+                    unsigned char* dst = stg + wn * I8_TILE_BYTES + (wm * 4 + mi) * 256 + (ni >> 1) * 128 + (lane >> 2) * 16 +
+                                         (ni & 1) * 8 + 2 * (lane & 3);
+#pragma unroll
+                    for (int sl = 0; sl < I8_NSL; ++sl) *reinterpret_cast<unsigned short*>(dst + sl * (TB * 32)) = (unsigned short)piece[sl];
+                }
+            }
+            __syncthreads();
+            signed char* S = g.S8 + (size_t)mat * i8_slices_per_matrix(g.nblk, g.sgroup);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint4* dstg = reinterpret_cast<uint4*>(S + i8_tile_off(4 * (k - k0) + 2 * h + c, ti, g.nblk));
+                const uint4* src = reinterpret_cast<const uint4*>(stg + c * I8_TILE_BYTES);
+#pragma unroll
+                for (int i = 0; i < I8_TILE_BYTES / 16 / 256; ++i) dstg[i * 256 + tid] = src[i * 256 + tid];
+            }
+            __syncthreads();                                       // the next pass refills the pipeline buffers
+        }
     }
     if (rhs != nullptr) {
 #pragma unroll

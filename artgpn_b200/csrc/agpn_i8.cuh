@@ -33,7 +33,6 @@
 #include "agpn_chol.cuh"
 #include "agpn_tma.cuh"     // cluster helpers, mbar_expect_tx
 
-#define I8_NSL 8
 #define I8_KB 32                                                 // bytes of K per stage = one kind::i8 K step
 #ifndef I8_STAGES
 #define I8_STAGES 3
@@ -44,12 +43,9 @@
 #define I8_CROW_BYTES (BN * 8 + 16)                              // padded C row: 16-byte accesses of a warp, one row per lane, conflict free
 #define I8_SMEM_BYTES (I8_STAGES * I8_STAGE_BYTES + TB * I8_CROW_BYTES + 1024)   // + slack for 1024-byte alignment
 #define I8_THREADS 192
-#define I8_Q (126.0 * 562949953421312.0)                         // 126 * 2^49
-#define I8_QMAX (127ll << 49)
-
-// bytes of slice storage per matrix: (128 sgroup / 32) K chunks x nblk row tiles x 8 slices x 4 KB
-__host__ __device__ __forceinline__ size_t i8_slices_per_matrix(int nblk, int sgroup) { return (size_t)(sgroup * 4) * nblk * I8_NSL * I8_A_BYTES; }
-__device__ __forceinline__ size_t i8_tile_off(int kc32, int rt, int nblk) { return ((size_t)kc32 * nblk + rt) * (I8_NSL * I8_A_BYTES); }
+#ifndef I8_PREFETCH
+#define I8_PREFETCH 0
+#endif
 
 // ---- row scales from the diagonal of the assembled matrix: qmul = Q / r, e = r / (126 2^24) ----------------------
 // grid (n_pad / 256, nmat)
@@ -82,24 +78,14 @@ __global__ void __launch_bounds__(256) i8_slice_kernel(CholArgs g, int k, int k0
         const double* src = A + (size_t)(rt * TB + row) * g.ld + (size_t)k * TB + ch * 16;
         unsigned w[I8_NSL][4];
 #pragma unroll
-        for (int s = 0; s < I8_NSL; ++s)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w[s][j] = 0u;
-#pragma unroll
         for (int c2 = 0; c2 < 8; ++c2) {
             const double2 v = *reinterpret_cast<const double2*>(src + 2 * c2);
+            unsigned piece[I8_NSL];
+            i8_digits2(v.x * f, v.y * f, piece);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int c = 2 * c2 + hh;
-                long long q = __double2ll_rn((hh ? v.y : v.x) * f);
-                q = q > I8_QMAX ? I8_QMAX : (q < -I8_QMAX ? -I8_QMAX : q);
-#pragma unroll
-                for (int s = I8_NSL - 1; s >= 1; --s) {
-                    const int dgt = (int)((q + 64) & 127) - 64;
-                    q = (q - dgt) >> 7;
-                    w[s][c >> 2] |= (unsigned)(dgt & 255) << (8 * (c & 3));
-                }
-                w[0][c >> 2] |= (unsigned)((int)q & 255) << (8 * (c & 3));
+            for (int s = 0; s < I8_NSL; ++s) {
+                if (c2 & 1) w[s][c2 >> 1] |= piece[s] << 16;
+                else w[s][c2 >> 1] = piece[s];
             }
         }
         const int kc32 = 4 * (k - k0) + (ch >> 1);
@@ -151,6 +137,9 @@ __device__ __forceinline__ void mbar_wait_long(unsigned addr, unsigned parity) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
@@ -231,6 +220,12 @@ syrk_i8_kernel(CholArgs g, int kfirst, int depth, int j0, int narrow) {
                 if (u > 0) mbar_wait(empty + 8 * s, (u - 1) & 1);
                 mbar_expect_tx(full + 8 * s, I8_STAGE_BYTES);
                 const unsigned dst = sbase + s * I8_STAGE_BYTES;
+#if I8_PREFETCH > 0
+                if (ks + I8_PREFETCH < nks) {                      // pull a later K step's digit planes into L2
+                    bulk_prefetch_l2(S + i8_tile_off(ks + I8_PREFETCH, ti, g.nblk) + rank * (4 * I8_A_BYTES), 4 * I8_A_BYTES);
+                    bulk_prefetch_l2(S + i8_tile_off(ks + I8_PREFETCH, tj, g.nblk) + rank * (4 * I8_A_BYTES), 4 * I8_A_BYTES);
+                }
+#endif
                 // my half of the A stage (slices 4 rank .. 4 rank + 3), delivered to both CTAs
                 bulk_g2s_mc(dst + rank * (4 * I8_A_BYTES), S + i8_tile_off(ks, ti, g.nblk) + rank * (4 * I8_A_BYTES), 4 * I8_A_BYTES,
                             full + 8 * s, (unsigned short)3);

@@ -1,6 +1,6 @@
-for W in 16 128; do for G in 8 16; do AGPN_SYRK=i8 AGPN_GROUP=$G python tools/sweep.py 2048 $W; done; done
-AGPN_GROUP=8 python tools/sweep.py 2048 16
-for G in 8 16 64; do AGPN_SYRK=i8 AGPN_GROUP=$G SWEEP_Q=3 python tools/sweep.py 8192 4 2; done
-AGPN_GROUP=8 SWEEP_Q=3 python tools/sweep.py 8192 4 2
-for G in 8 64; do AGPN_SYRK=i8 AGPN_GROUP=$G SWEEP_Q=3 python tools/sweep.py 8192 32 1; done
-AGPN_GROUP=8 SWEEP_Q=3 python tools/sweep.py 8192 32 1
+for L in "" artgpn_b200/variants/lib_pf4.so artgpn_b200/variants/lib_pf8.so; do
+  echo "lib=$L"
+  AGPN_LIB=$L python tools/sweep.py 2048 128
+  AGPN_LIB=$L python tools/sweep.py 2048 16
+done
+for S in 1 2 3 4 8; do AGPN_STREAMS=$S python tools/sweep.py 2048 128; AGPN_STREAMS=$S python tools/sweep.py 2048 16; done

@@ -84,3 +84,33 @@ if len(sys.argv) > 1 and sys.argv[1] == "prof":
             mode, group, ms_step, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], sm, n.tolist(), sn), flush=True)
         del net
         torch.cuda.empty_cache()
+
+if len(sys.argv) > 1 and sys.argv[1] == "fuse":
+    for N, W, group in ((300, 5, None), (1000, 6, None), (2048, 8, None), (2048, 8, 4), (1000, 6, 3)):
+        res = {}
+        for fuse in ("0", "1"):
+            os.environ["AGPN_I8_FUSE"] = fuse
+            net, th = make(N, W, "i8", group=group)
+            res[fuse] = net.log_likelihood_batch(th).cpu().numpy()
+        ref_net, th = make(N, W, "dmma")
+        ref = ref_net.log_likelihood_batch(th).cpu().numpy()
+        print("N=%d W=%d group=%s: fused == separate slicing: %s ; max rel diff vs dmma %.3e" % (
+            N, W, group, bool(np.array_equal(res["0"], res["1"])), np.max(np.abs(res["1"] - ref) / np.abs(ref))), flush=True)
+    for fuse in ("0", "1"):
+        os.environ["AGPN_I8_FUSE"] = fuse
+        for W in (128, 16):
+            net, th = make(2048, W, "i8")
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < 0.5:
+                net.log_likelihood_batch(th)
+                torch.cuda.synchronize()
+            ms = timeit(net, th, steps=8)
+            net.set_profiling(True)
+            net.log_likelihood_batch(th)
+            pm, n = net.phase_times()
+            sm, sn = net.slice_times()
+            net.set_profiling(False)
+            print("fuse=%s W=%d: %.3f ms/step %.1f evals/s | asm %.2f diag %.2f trsm %.2f syrk %.2f slice %.2f" % (
+                fuse, W, ms, W / ms * 1e3, pm[1], pm[2], pm[3], pm[4], sm), flush=True)
+            del net
+            torch.cuda.empty_cache()
