@@ -97,6 +97,8 @@ struct agpn_ctx {
     // INT8-sliced trailing update (agpn_i8.cuh), the default: bit 0 = narrow updates, bit 1 = wide updates
     // (AGPN_SYRK = i8 | i8_narrow | i8_wide; dmma | cpasync | tma* select the FP64 tensor instruction everywhere)
     int i8_which = 3;
+    bool i8_persist = true;        // AGPN_I8_PERSIST=0: one CTA pair per tile instead of persistent clusters
+    int i8_clusters = 74;          // persistent clusters per launch = SMs / 2
     bool fuse_slices = true;       // AGPN_I8_FUSE=0: separate i8_slice_kernel after every panel solve
     int i8_group = 8;              // group of the INT8 path: all block columns (pure left-looking) unless AGPN_GROUP is given
     signed char* d_S8 = nullptr;   // [cap_mats] digit planes of one group of block columns
@@ -191,6 +193,7 @@ static int set_kernel_attrs(agpn_ctx* c) {
     CUDA_TRY(cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(syrk_i8_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
     // function attributes are per function (not per context): always allow the largest K0 configuration
     {
         cudaFuncAttributes fa;
@@ -227,6 +230,13 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
         c->tma_which = strcmp(e, "tma_narrow") == 0 ? 1 : (strcmp(e, "tma_wide") == 0 ? 2 : 3); }
     c->i8_which = i8_mode_from_env();
     if (const char* e = getenv("AGPN_I8_FUSE")) c->fuse_slices = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_I8_PERSIST")) c->i8_persist = atoi(e) != 0;
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        c->i8_clusters = sms / 2 > 0 ? sms / 2 : 1;
+        if (const char* e = getenv("AGPN_I8_CLUSTERS")) if (atoi(e) > 0) c->i8_clusters = atoi(e);
+    }
     // the INT8 path is fastest purely left-looking (every C tile is visited once, measured: C3 25.1 ms with one group
     // of 16 vs 26.0 with groups of 8; C4 213 vs 249 ms); int32 accumulators bound the depth to 256 block columns
     c->i8_group = c->group_fixed ? c->group : c->nblk;
@@ -472,7 +482,11 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
         for (int k = k0; k < kend; ++k) {
             if (k > k0) {
                 PhaseScope ps(c, st, PH_SYRK, cur);
-                if (i8 & 1)
+                if ((i8 & 1) && c->i8_persist) {
+                    const int ntl = g.nblk - k, total = ntl * g.nmat;
+                    const int ncl = total < c->i8_clusters ? total : c->i8_clusters;
+                    syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, ntl, total);
+                } else if (i8 & 1)
                     syrk_i8_kernel<<<dim3(2 * (g.nblk - k), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
                 else if (c->maps_valid && (c->tma_which & 1))
                     syrk_tma_kernel<<<dim3(2 * (g.nblk - k), g.nmat), TMA_THREADS, TMA_SMEM_BYTES, st>>>(c->tmA, c->tmB, g, k0, k - k0, k, 1, c->tma_mc);
@@ -504,7 +518,11 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
         const int nt = g.nblk - kend;
         if (nt > 0) {
             PhaseScope ps(c, st, PH_SYRK, cur);
-            if (i8 & 2)
+            if ((i8 & 2) && c->i8_persist) {
+                const int ntl = nt * (nt + 1) / 2, total = ntl * g.nmat;
+                const int ncl = total < c->i8_clusters ? total : c->i8_clusters;
+                syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, kend - k0, kend, 0, ntl, total);
+            } else if (i8 & 2)
                 syrk_i8_kernel<<<dim3(nt * (nt + 1), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
             else if (c->maps_valid && (c->tma_which & 2))
                 syrk_tma_kernel<<<dim3(nt * (nt + 1), g.nmat), TMA_THREADS, TMA_SMEM_BYTES, st>>>(c->tmA, c->tmB, g, k0, kend - k0, kend, 0, c->tma_mc);
@@ -1154,6 +1172,7 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     tmp.group_eff = (tmp.group_fixed || (long long)nmat * (n_pad / TB) >= 384) ? tmp.group : 2;
     tmp.i8_which = i8_mode_from_env();
     if (const char* e = getenv("AGPN_I8_FUSE")) tmp.fuse_slices = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_I8_PERSIST")) tmp.i8_persist = atoi(e) != 0;
     g.keep_factor = 1;                                   // the caller reads L
     signed char* d_s8 = nullptr;
     double* d_rs = nullptr;

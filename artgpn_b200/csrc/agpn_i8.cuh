@@ -358,3 +358,205 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int* sink) {
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }
+
+// ---- persistent variant: a cluster walks over many tiles ------------------------------------------------------------
+// Same tile kernel, but the per-tile fixed cost (CTA launch, TMEM allocation, barrier set-up, two cluster syncs and
+// above all the pipeline fill from L2 / DRAM) is paid once per CTA instead of once per tile: the producer warp runs
+// ahead into the next tile's K steps while the epilogue warps drain the accumulators, the stage / phase counters run
+// on across tiles, and one extra mbarrier (`tfree`) tells the MMA thread when TMEM may be overwritten.
+//   grid.x = 2 * clusters (<= one CTA per SM), tiles of the launch: (matrix, tile) pairs, tile index fastest
+//   ntiles = tiles per matrix: narrow: nblk - j0 (tiles (j0 + t, j0)); wide: nt (nt + 1) / 2
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles, int total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[2 * I8_STAGES + 3];
+    __shared__ unsigned tmem_base_s;
+    __shared__ double ecol[2][BN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = cluster_ctarank();
+    const int h = (int)rank;                                        // which 64-column half of the tile
+    const int n = g.nblk * TB;
+    const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+    const unsigned sraw = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned sbase = (sraw + 1023u) & ~1023u;
+    const unsigned cs = sbase + I8_STAGES * I8_STAGE_BYTES;         // C tile, rows of I8_CROW_BYTES
+    const unsigned full = (unsigned)__cvta_generic_to_shared(bars);
+    const unsigned empty = full + 8 * I8_STAGES, done = full + 16 * I8_STAGES, cfull = done + 8, tfree = done + 16;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < I8_STAGES; ++s) {
+            mbar_init(full + 8 * s, 1);
+            mbar_init(empty + 8 * s, 2);                            // one tcgen05.commit from each CTA of the pair
+        }
+        mbar_init(done, 1);
+        mbar_init(cfull, 1);
+        mbar_init(tfree, 4);                                        // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                             // both CTAs' barriers exist before any multicast / remote commit
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem = tmem_base_s;
+    const int nks = depth * (TB / I8_KB);
+
+    // tile w -> (matrix, block row ti, block column tj)
+    auto decode = [&](int w, int& mat, int& ti, int& tj, bool& diag) {
+        mat = w / ntiles;
+        const int t = w - mat * ntiles;
+        int bi, bj;
+        if (narrow) {
+            bi = t;
+            bj = 0;
+        } else {
+            bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+            while (bi * (bi + 1) / 2 > t) --bi;
+            bj = t - bi * (bi + 1) / 2;
+        }
+        ti = j0 + bi;
+        tj = j0 + bj;
+        diag = bi == bj;
+    };
+
+    if (warp == 0) {
+        // ---------------- producer: runs ahead across tile boundaries ----------------
+        if (lane == 0) {
+            unsigned it = 0;                                        // K steps issued so far (all tiles)
+            for (int w = cl; w < total; w += ncl) {
+                int mat, ti, tj;
+                bool diag;
+                decode(w, mat, ti, tj, diag);
+                const signed char* S = g.S8 + (size_t)mat * i8_slices_per_matrix(g.nblk, g.sgroup);
+                for (int ks = 0; ks < nks; ++ks, ++it) {
+                    const unsigned s = it % I8_STAGES, u = it / I8_STAGES;
+                    if (u > 0) mbar_wait(empty + 8 * s, (u - 1) & 1);
+                    mbar_expect_tx(full + 8 * s, I8_STAGE_BYTES);
+                    const unsigned dst = sbase + s * I8_STAGE_BYTES;
+                    bulk_g2s_mc(dst + rank * (4 * I8_A_BYTES), S + i8_tile_off(ks, ti, g.nblk) + rank * (4 * I8_A_BYTES), 4 * I8_A_BYTES,
+                                full + 8 * s, (unsigned short)3);
+                    const signed char* bsrc = S + i8_tile_off(ks, tj, g.nblk) + h * I8_B_BYTES;
+#pragma unroll
+                    for (int sl = 0; sl < I8_NSL; ++sl)
+                        bulk_g2s(dst + I8_NSL * I8_A_BYTES + sl * I8_B_BYTES, bsrc + sl * I8_A_BYTES, I8_B_BYTES, full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TB >> 4) << 24);
+            unsigned it = 0, tile = 0;
+            for (int w = cl; w < total; w += ncl, ++tile) {
+                if (tile > 0) {                                     // the epilogue has drained the previous tile's accumulators
+                    mbar_wait(tfree, (tile - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                }
+                for (int ks = 0; ks < nks; ++ks, ++it) {
+                    const unsigned s = it % I8_STAGES;
+                    mbar_wait(full + 8 * s, (it / I8_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const unsigned a0 = sbase + s * I8_STAGE_BYTES, b0 = a0 + I8_NSL * I8_A_BYTES;
+                    const unsigned accum0 = ks > 0 ? 1u : 0u;
+                    I8_MMA(0, 0, 4, true);
+                    I8_MMA(0, 4, 4, true);
+                    I8_MMA(1, 0, 4, false);
+                    I8_MMA(1, 4, 3, false);
+                    I8_MMA(2, 0, 4, false);
+                    I8_MMA(2, 4, 2, false);
+                    I8_MMA(3, 0, 4, false);
+                    I8_MMA(3, 4, 1, false);
+                    I8_MMA(4, 0, 4, false);
+                    I8_MMA(5, 0, 3, false);
+                    I8_MMA(6, 0, 2, false);
+                    I8_MMA(7, 0, 1, false);
+                    umma_commit_mc(empty + 8 * s, (unsigned short)3);
+                }
+                umma_commit(done);
+            }
+        }
+    } else {
+        // ---------------- epilogue: thread = one row of the tile (TMEM lane) ----------------
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int et = tid - 64;                                    // 0 .. 127 among the epilogue threads
+        const unsigned crow = cs + row * I8_CROW_BYTES;
+        double* cgen = reinterpret_cast<double*>(smem_raw + (crow - sraw));
+        const unsigned tlane = tmem + ((unsigned)(q * 32) << 16);
+        unsigned tile = 0;
+        for (int w = cl; w < total; w += ncl, ++tile) {
+            int mat, ti, tj;
+            bool diag;
+            decode(w, mat, ti, tj, diag);
+            const bool half_tile = diag && h == 1;                  // rows 0..63 lie strictly above the diagonal
+            const bool skip = half_tile && q < 2;                   // warp-uniform
+            const double* esc = g.rscale + (size_t)mat * 2 * n + n;
+            double* Crow = g.A + (size_t)mat * g.mat_stride + (size_t)(ti * TB + row) * g.ld + (size_t)tj * TB + h * BN;
+            const int eb = tile & 1;
+            if (et < BN) ecol[eb][et] = 0.5 * esc[tj * TB + h * BN + et];
+            if (et == 0) mbar_expect_tx(cfull, (half_tile ? TB / 2 : TB) * BN * 8);
+            if (!skip) bulk_g2s(crow, Crow, BN * 8, cfull);
+            const double ei = esc[ti * TB + row];
+            named_bar_sync(1, 128);                                 // ecol[eb] visible to the four epilogue warps
+            mbar_wait(done, tile & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            mbar_wait(cfull, tile & 1);                             // every epilogue thread: nobody may post the next tile's bytes into this phase
+            if (!skip) {
+#pragma unroll 1
+                for (int c8 = 0; c8 < BN / 8; ++c8) {
+                    int v[I8_NSL][8];
+#pragma unroll
+                    for (int d = 0; d < I8_NSL; ++d) tmem_ld8(tlane + d * BN + c8 * 8, v[d]);
+                    tmem_ld_wait();
+                    if (c8 == BN / 8 - 1) {                         // last read of the accumulators: hand TMEM back
+                        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tfree);
+                    }
+#pragma unroll
+                    for (int j2 = 0; j2 < 8; j2 += 2) {
+                        double2 cc = *reinterpret_cast<double2*>(cgen + c8 * 8 + j2);
+                        double r2[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int j = j2 + u;
+                            double H = i8_i2d(v[0][j]), Lo = i8_i2d(v[4][j]);
+#pragma unroll
+                            for (int d = 1; d < 4; ++d) {
+                                H = fma(H, 128.0, i8_i2d(v[d][j]));
+                                Lo = fma(Lo, 128.0, i8_i2d(v[4 + d][j]));
+                            }
+                            const double val = fma(H, 268435456.0, Lo);
+                            r2[u] = (val * ei) * ecol[eb][c8 * 8 + j];
+                        }
+                        cc.x -= r2[0];
+                        cc.y -= r2[1];
+                        *reinterpret_cast<double2*>(cgen + c8 * 8 + j2) = cc;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                bulk_s2g(Crow, crow, BN * 8);
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");       // the row buffer is free for the next tile's load
+            } else {
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tfree);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();        // nobody leaves while the peer may still multicast into / commit onto this CTA
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}

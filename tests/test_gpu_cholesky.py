@@ -28,18 +28,22 @@ def _spd(rng, nmat, n, cond_jitter):
     return X @ X.transpose(0, 2, 1) + cond_jitter * np.eye(n)
 
 
-@pytest.fixture(params=["i8", "i8:2", "i8_wide:3", "i8_narrow:4", "cpasync", "cpasync:2", "tma", "tma_nomc"])
+@pytest.fixture(params=["i8", "i8:2", "i8_wide:3", "i8_narrow:4", "i8:3:pertile", "cpasync", "cpasync:2", "tma", "tma_nomc"])
 def syrk_variant(request, monkeypatch):
     """Trailing-update kernel (AGPN_SYRK[:AGPN_GROUP], read per call here): the INT8-sliced tcgen05 kernel
     (default; left-looking, or with groups so that narrow and wide updates both run on it, or only one of
-    them), the FP64 cp.async + mbarrier DMMA kernel, or the TMA (cp.async.bulk.tensor) producer-warp DMMA
+    them; persistent clusters or one CTA pair per tile), the FP64 cp.async + mbarrier DMMA kernel, or the TMA (cp.async.bulk.tensor) producer-warp DMMA
     kernel with / without cluster multicast."""
-    kind, _, group = request.param.partition(":")
+    kind, group, pertile = (request.param.split(":") + ["", ""])[:3]
     monkeypatch.setenv("AGPN_SYRK", kind)
     if group:
         monkeypatch.setenv("AGPN_GROUP", group)
     else:
         monkeypatch.delenv("AGPN_GROUP", raising=False)
+    if pertile:
+        monkeypatch.setenv("AGPN_I8_PERSIST", "0")      # one CTA pair per tile instead of persistent clusters
+    else:
+        monkeypatch.delenv("AGPN_I8_PERSIST", raising=False)
     return request.param
 
 

@@ -108,6 +108,28 @@ def test_c3_update_paths_agree_and_match_oracle(monkeypatch):
         got[(mode, group)] = net.log_likelihood_batch(theta)
         assert np.array_equal(net.log_likelihood_batch(theta), got[(mode, group)])
         net.close()
+    # the panel solve writes the digit planes itself (default); the separate slicing kernel gives the same bits
+    monkeypatch.setenv("AGPN_SYRK", "i8")
+    monkeypatch.delenv("AGPN_GROUP", raising=False)
+    monkeypatch.setenv("AGPN_I8_FUSE", "0")
+    net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+    net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], 3, 2, "Constant")[:3])
+    assert np.array_equal(net.log_likelihood_batch(theta), got[("i8", None)])
+    net.close()
+    monkeypatch.delenv("AGPN_I8_FUSE", raising=False)
+    # persistent clusters walking over the tiles (default) vs one CTA pair per tile: same bits, also with wide updates
+    for group in (None, "4"):
+        monkeypatch.setenv("AGPN_I8_PERSIST", "0")
+        if group:
+            monkeypatch.setenv("AGPN_GROUP", group)
+        else:
+            monkeypatch.delenv("AGPN_GROUP", raising=False)
+        net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+        net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], 3, 2, "Constant")[:3])
+        assert np.array_equal(net.log_likelihood_batch(theta), got[("i8", group)])
+        net.close()
+    monkeypatch.delenv("AGPN_I8_PERSIST", raising=False)
+    monkeypatch.delenv("AGPN_GROUP", raising=False)
     ref = got[("dmma", None)]
     for k, v in got.items():
         assert abs(v[2] - exp) <= 1e-9 * abs(exp), (k, v[2], exp)

@@ -114,3 +114,32 @@ if len(sys.argv) > 1 and sys.argv[1] == "fuse":
                 fuse, W, ms, W / ms * 1e3, pm[1], pm[2], pm[3], pm[4], sm), flush=True)
             del net
             torch.cuda.empty_cache()
+
+if len(sys.argv) > 1 and sys.argv[1] == "persist":
+    for N, W, group in ((300, 5, None), (1000, 6, None), (2048, 8, None), (2048, 8, 4), (1000, 6, 3), (2048, 40, None)):
+        res = {}
+        for pe in ("0", "1"):
+            os.environ["AGPN_I8_PERSIST"] = pe
+            net, th = make(N, W, "i8", group=group)
+            res[pe] = net.log_likelihood_batch(th).cpu().numpy()
+            again = net.log_likelihood_batch(th).cpu().numpy()
+            assert np.array_equal(again, res[pe])
+        print("N=%d W=%d group=%s: persistent == per-tile kernel: %s  ll[0]=%.15g" % (
+            N, W, group, bool(np.array_equal(res["0"], res["1"])), res["1"][0]), flush=True)
+    for pe in ("0", "1"):
+        os.environ["AGPN_I8_PERSIST"] = pe
+        for N, W in ((2048, 128), (2048, 16), (8192, 4)):
+            net, th = make(N, W, "i8", q=3 if N == 8192 else 2)
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < 0.5:
+                net.log_likelihood_batch(th)
+                torch.cuda.synchronize()
+            ms = timeit(net, th, steps=8 if N == 2048 else 2)
+            net.set_profiling(True)
+            net.log_likelihood_batch(th)
+            pm, n = net.phase_times()
+            net.set_profiling(False)
+            print("persist=%s N=%d W=%d: %.3f ms/step %.1f evals/s | asm %.2f diag %.2f trsm %.2f syrk %.2f" % (
+                pe, N, W, ms, W / ms * 1e3, pm[1], pm[2], pm[3], pm[4]), flush=True)
+            del net
+            torch.cuda.empty_cache()
