@@ -69,24 +69,32 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // fields u = a + 64.  Returns the eight digits of two values as eight 16-bit pieces (value 0 in the low byte).
 #define I8_NSL 8
 #define I8_Q (126.0 * 562949953421312.0)                         // 126 * 2^49
-#define I8_QMAXF (127.0 * 562949953421312.0)
 #define I8_DIGIT_BIAS 0x0001020408102040ll                       // 64 * sum_{j<7} 128^j
 #define I8_TILE_BYTES (I8_NSL * TB * 32)                         // digit planes of 128 rows x 32 columns: 32 KB
+// fields (x >> sh) & 127 of two values, two digits at a time, as bytes [v0 digit a, v1 digit a, v0 digit b, v1 digit b];
+// the bias removal u - 64 (mod 256) on all four bytes at once: v = u ^ 0x40, byte = v | ((v & 0x40) << 1)
+__device__ __forceinline__ unsigned i8_pack4(unsigned a0, unsigned a1, unsigned b0, unsigned b1, unsigned keep, unsigned flip, unsigned sign) {
+    const unsigned lo = __byte_perm(a0, a1, 0x0040), hi = __byte_perm(b0, b1, 0x0040);
+    const unsigned v = (__byte_perm(lo, hi, 0x5410) & keep) ^ flip;
+    return v | ((v << 1) & sign);
+}
 __device__ __forceinline__ void i8_digits2(double x0, double x1, unsigned (&piece)[I8_NSL]) {
-    x0 = fmin(fmax(x0, -I8_QMAXF), I8_QMAXF);                    // NaN -> -QMAX: harmless, the block is flagged elsewhere
-    x1 = fmin(fmax(x1, -I8_QMAXF), I8_QMAXF);
+    // |x| <= 126 2^49 (1 + 1e-9) for every factorisable matrix (sum_k L_ik^2 = K_ii); a block that is not positive
+    // definite or not finite is flagged by the factorisation and its digits only have to be harmless: NaN converts
+    // to 0, overflow saturates / wraps
     const long long q0 = __double2ll_rn(x0) + I8_DIGIT_BIAS, q1 = __double2ll_rn(x1) + I8_DIGIT_BIAS;
     const unsigned l0 = (unsigned)q0, l1 = (unsigned)q1;
     const unsigned h0 = (unsigned)(q0 >> 28), h1 = (unsigned)(q1 >> 28);      // digits 4 .. 7 (bits 28 .. 56 + sign)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        // slice 7 - j holds digit j (weight 128^j)
-        piece[7 - j] = ((((l0 >> (7 * j)) & 127u) + 192u) & 255u) | (((((l1 >> (7 * j)) & 127u) + 192u) & 255u) << 8);
-    }
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-        piece[3 - j] = ((((h0 >> (7 * j)) & 127u) + 192u) & 255u) | (((((h1 >> (7 * j)) & 127u) + 192u) & 255u) << 8);
-    piece[0] = ((unsigned)((int)h0 >> 21) & 255u) | (((unsigned)((int)h1 >> 21) & 255u) << 8);
+    // slice 7 - j holds digit j (weight 128^j); words: (slice 7 | slice 6 << 16), (5 | 4), (3 | 2), (1 | 0)
+    const unsigned w76 = i8_pack4(l0, l1, l0 >> 7, l1 >> 7, 0x7F7F7F7Fu, 0x40404040u, 0x80808080u);
+    const unsigned w54 = i8_pack4(l0 >> 14, l1 >> 14, l0 >> 21, l1 >> 21, 0x7F7F7F7Fu, 0x40404040u, 0x80808080u);
+    const unsigned w32 = i8_pack4(h0, h1, h0 >> 7, h1 >> 7, 0x7F7F7F7Fu, 0x40404040u, 0x80808080u);
+    // digit 6 and the signed rest (bits 49 ..: no bias on it)
+    const unsigned w10 = i8_pack4(h0 >> 14, h1 >> 14, (unsigned)((int)h0 >> 21), (unsigned)((int)h1 >> 21), 0xFFFF7F7Fu, 0x00004040u, 0x00008080u);
+    piece[7] = w76 & 0xFFFFu; piece[6] = w76 >> 16;
+    piece[5] = w54 & 0xFFFFu; piece[4] = w54 >> 16;
+    piece[3] = w32 & 0xFFFFu; piece[2] = w32 >> 16;
+    piece[1] = w10 & 0xFFFFu; piece[0] = w10 >> 16;
 }
 __host__ __device__ __forceinline__ size_t i8_slices_per_matrix(int nblk, int sgroup) { return (size_t)(sgroup * 4) * nblk * I8_TILE_BYTES; }
 __host__ __device__ __forceinline__ size_t i8_tile_off(int kc32, int rt, int nblk) { return ((size_t)kc32 * nblk + rt) * I8_TILE_BYTES; }

@@ -1,6 +1,2 @@
-for L in "" artgpn_b200/variants/lib_pf4.so artgpn_b200/variants/lib_pf8.so; do
-  echo "lib=$L"
-  AGPN_LIB=$L python tools/sweep.py 2048 128
-  AGPN_LIB=$L python tools/sweep.py 2048 16
-done
-for S in 1 2 3 4 8; do AGPN_STREAMS=$S python tools/sweep.py 2048 128; AGPN_STREAMS=$S python tools/sweep.py 2048 16; done
+for F in 1 0; do for S in 6 8; do echo "fuse=$F streams=$S"; AGPN_I8_FUSE=$F AGPN_STREAMS=$S python tools/sweep.py 2048 128; AGPN_I8_FUSE=$F AGPN_STREAMS=$S python tools/sweep.py 2048 16; done; done
+for C in 60 66 70; do echo "clusters=$C"; AGPN_I8_CLUSTERS=$C python tools/sweep.py 2048 128; done
