@@ -103,7 +103,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -344,7 +344,7 @@ def main():
             syrk_tops = 36.0 * syrk_tf if syrk_tf else None
             roofline = {
                 "bound": "tensor",
-                "kernel": "syrk_i8_kernel: trailing update as exact integer products of 8 x 7-bit slices, "
+                "kernel": "syrk_i8_persistent_kernel: trailing update as exact integer products of 8 x 7-bit slices, "
                           "tcgen05.mma.kind::i8 with TMEM int32 accumulators (all launches of a step)",
                 "achieved": syrk_tops, "peak": i8_peak, "unit": "TOP/s",
                 "frac": (syrk_tops / i8_peak) if syrk_tops else None,
@@ -354,7 +354,7 @@ def main():
                 "ops_per_step": (36.0 * W_local * p * syrk_tiles * 2.0 * 128 ** 3),
                 "ms": float(phase[4]), "launches": int(nl[4]), "share_of_step_ms": syrk_share,
                 "traffic": syrk_traffic,
-                "traffic_note": "DRAM bytes of all syrk_i8_kernel launches of one step, ncu pass in profiles/ (scaled by walkers)",
+                "traffic_note": "DRAM bytes of all syrk_i8_persistent_kernel launches of one step, ncu pass in profiles/ (scaled by walkers)",
                 "fp64_equivalent": {"tflops": syrk_tf, "dmma_peak_tflops": dmma_peak,
                                     "ratio_to_dmma_peak": (syrk_tf / dmma_peak) if syrk_tf else None,
                                     "note": "the same update on the FP64 tensor instruction cannot exceed 1.0"},

@@ -16,7 +16,7 @@ for r in rows:
         agg[name]["bytes"] += v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
     elif m == "gpu__time_duration.sum":
         agg[name]["launches"] += 1
-syrk = "syrk_i8_kernel" if upath else "syrk_kernel"
+syrk = ("syrk_i8_persistent_kernel" if "syrk_i8_persistent_kernel" in agg else "syrk_i8_kernel") if upath else "syrk_kernel"
 steps = agg[syrk]["launches"] / per_step
 chol = sum(agg[k]["bytes"] for k in ("potrf_diag_kernel", "trsm_kernel", "i8_slice_kernel", "i8_rowscale_kernel", syrk)) / steps
 out = {
