@@ -49,6 +49,7 @@ _SIGNATURES = {
     "agpn_set_profiling": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "agpn_phase_ms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "agpn_update_path": (ctypes.c_int, [c_void_p]),
+    "agpn_predict_path": (ctypes.c_int, [c_void_p]),
     "agpn_slice_ms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
 }
 

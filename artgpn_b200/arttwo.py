@@ -451,6 +451,11 @@ class network(object):
         INT8-sliced path (chosen at construction from AGPN_SYRK)."""
         return int(_lib.load().agpn_update_path(self._ctx()))
 
+    def predict_path(self):
+        """1: the last prediction ran on the factorisation kernels (K* appended as block rows, INT8-sliced updates);
+        0: on the stand-alone FP64 predict_kernel (AGPN_PREDICT=dmma or automatic fall-back); -1: none yet."""
+        return int(_lib.load().agpn_predict_path(self._ctx()))
+
     def slice_times(self):
         """(ms, launches) of the digit-slicing kernels of the last profiled log_likelihood_batch."""
         ms = np.zeros(1)

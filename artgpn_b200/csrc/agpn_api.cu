@@ -77,6 +77,14 @@ struct agpn_ctx {
     double* d_V = nullptr;
     size_t cap_M = 0;
     double* d_pred = nullptr;  // tstar | mstar | kss | mean | std, 5 * cap_M
+    // prediction on the factorisation kernels: [K ; K*] stacked (T x n_pad), its digit planes, rhs | row scales | flag
+    bool predict_dmma = false;  // AGPN_PREDICT=dmma: the stand-alone predict_kernel (FP64 tensor instruction) only
+    bool predict_test_wrap = false;   // AGPN_I8_TEST_WRAP=1 (fault injection for the tests): unit row scales for the K* rows
+    int last_predict_path = -1; // 1: stacked factorisation path, 0: predict_kernel
+    size_t cap_paug = 0, cap_ps8 = 0, cap_pvec = 0;
+    double* d_paug = nullptr;
+    signed char* d_ps8 = nullptr;
+    double* d_pvec = nullptr;
     size_t cap_aug = 0;        // augmented [K . ; K* K**] matrix of agpn_predict_cov, doubles
     double* d_aug = nullptr;
     size_t cap_augv = 0;
@@ -231,6 +239,8 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     c->i8_which = i8_mode_from_env();
     if (const char* e = getenv("AGPN_I8_FUSE")) c->fuse_slices = atoi(e) != 0;
     if (const char* e = getenv("AGPN_I8_PERSIST")) c->i8_persist = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_PREDICT")) c->predict_dmma = strcmp(e, "dmma") == 0;
+    if (const char* e = getenv("AGPN_I8_TEST_WRAP")) c->predict_test_wrap = atoi(e) != 0;
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -298,6 +308,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_A); cudaFree(c->d_Linv); cudaFree(c->d_rhs); cudaFree(c->d_logdet); cudaFree(c->d_quad);
     cudaFree(c->d_info); cudaFree(c->d_theta); cudaFree(c->d_out); cudaFree(c->d_status);
     cudaFree(c->d_S8); cudaFree(c->d_rscale);
+    cudaFree(c->d_paug); cudaFree(c->d_ps8); cudaFree(c->d_pvec);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
     delete c;
     return 0;
@@ -383,6 +394,7 @@ extern "C" int agpn_slice_ms(agpn_ctx* c, double* ms, long long* launches) {
 }
 
 extern "C" int agpn_update_path(const agpn_ctx* c) { return c ? c->i8_which : -1; }
+extern "C" int agpn_predict_path(const agpn_ctx* c) { return c ? c->last_predict_path : -1; }
 
 // ---- profiling helpers ---------------------------------------------------------------------
 struct PhaseScope {
@@ -466,7 +478,7 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
 // the (narrow) update from the group's earlier columns, then its diagonal block is factorised and
 // its panel solved; after the group the whole trailing matrix takes ONE update of depth
 // 128 * group (wide).  group = 1 is the plain right-looking algorithm.
-static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor, int kstop = -1) {
+static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor, int kstop = -1, bool no_trailing = false) {
     size_t local_cursor = 0;
     size_t& cur = cursor ? *cursor : local_cursor;
     // few small matrices: the left-looking narrow updates of a deep group have too few CTAs to fill the GPU
@@ -499,7 +511,8 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
                 potrf_diag_kernel<<<g.nmat, 256, POTRF_SMEM_BYTES, st>>>(g, k);
                 LAUNCH_CHECK();
             }
-            const bool need_slices = k < g.nblk - 1 && ((((i8 & 1) && k + 1 < kend)) || ((i8 & 2) && kend < g.nblk));
+            const bool trailing = kend < g.nblk && !(no_trailing && kend == kstop);
+            const bool need_slices = k < g.nblk - 1 && ((((i8 & 1) && k + 1 < kend)) || ((i8 & 2) && trailing));
             // the panel solve writes the digit planes itself; the FP64 panel is stored only if somebody reads it
             // (a DMMA update of a mixed mode, or a caller that wants the factor: g.keep_factor)
             const int tflags = (need_slices && c->fuse_slices) ? (1 | ((i8 == 3 && !g.keep_factor) ? 2 : 0)) : 0;
@@ -515,7 +528,8 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
                 LAUNCH_CHECK();
             }
         }
-        const int nt = g.nblk - kend;
+        // no_trailing: the columns right of kstop do not exist (K* rows appended below a training block)
+        const int nt = (no_trailing && kend == kstop) ? 0 : g.nblk - kend;
         if (nt > 0) {
             PhaseScope ps(c, st, PH_SYRK, cur);
             if ((i8 & 2) && c->i8_persist) {
@@ -646,7 +660,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         // row scales r_i = sqrt(K_ii) >= |L_ik| from the assembled diagonal, before the factorisation overwrites it
         g.S8 = c->d_S8; g.rscale = c->d_rscale; g.sgroup = c->sgroup;
         PhaseScope ps(c, st, PH_SLICE, cur);
-        i8_rowscale_kernel<<<dim3((c->npad + 255) / 256, nmat), 256, 0, st>>>(g);
+        i8_rowscale_kernel<<<dim3((c->npad + 255) / 256, nmat), 256, 0, st>>>(g, c->npad, nullptr, 0);
         LAUNCH_CHECK();
     }
     const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
@@ -908,6 +922,85 @@ extern "C" int agpn_predict_slice(agpn_ctx* c, const double* theta, int series, 
     return predict_impl(c, theta, series, M, tstar, true, grid_mean, grid_t0, mean_out, std_out, status, stream);
 }
 
+// Prediction on the factorisation kernels.  V = K* L^-T is what the blocked Cholesky computes for block rows appended
+// below K: [K ; K*] (T x n_pad, no columns right of the training block) is eliminated left-looking over the training
+// block columns only; the K* rows take the same INT8-sliced updates (row scale sqrt(k**_ii) >= |V_i|) and the same
+// panel solves, the folded forward solve leaves -K* K^-1 r in the appended part of the right-hand side, and one pass
+// over V gives the row sums of squares (arttwo.py:371-395).  *wrapped: an entry exceeded its row scale (a covariance
+// that is not positive semi-definite jointly, e.g. the WhiteNoise square-lag quirk) -> the caller uses predict_kernel.
+static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, const double* d_ts, const double* d_ms, double* d_kss,
+                           double* d_mu, double* d_sd, int* d_kflag, cudaStream_t st, int* wrapped, int* unavailable) {
+    const size_t np = (size_t)c->npad;
+    const size_t T = np + Mpad;
+    const int nrt = (int)(T / TB);
+    const int sgroup = c->nblk < 2 ? 2 : c->nblk;
+    const size_t s8_bytes = c->nblk > 1 ? i8_slices_per_matrix(nrt, sgroup) : 0;
+    *wrapped = 0;
+    *unavailable = 0;
+    if (T * np > c->cap_paug) {
+        cudaFree(c->d_paug);
+        c->d_paug = nullptr;
+        c->cap_paug = 0;
+        if (cudaMalloc(&c->d_paug, sizeof(double) * T * np) != cudaSuccess) { cudaGetLastError(); *unavailable = 1; return 0; }
+        c->cap_paug = T * np;
+    }
+    if (s8_bytes > c->cap_ps8) {
+        cudaFree(c->d_ps8);
+        c->d_ps8 = nullptr;
+        c->cap_ps8 = 0;
+        if (cudaMalloc(&c->d_ps8, s8_bytes) != cudaSuccess) { cudaGetLastError(); *unavailable = 1; return 0; }
+        c->cap_ps8 = s8_bytes;
+    }
+    if (3 * T + 2 > c->cap_pvec) {
+        cudaFree(c->d_pvec);
+        c->d_pvec = nullptr;
+        c->cap_pvec = 0;
+        if (cudaMalloc(&c->d_pvec, sizeof(double) * (3 * T + 2)) != cudaSuccess) { cudaGetLastError(); *unavailable = 1; return 0; }
+        c->cap_pvec = 3 * T + 2;
+    }
+    double* d_rhs = c->d_pvec;                  // [T]: residual | 0  ->  z | -K* K^-1 r
+    double* d_rs = c->d_pvec + T;               // [2][T] row scales
+    int* d_flag = reinterpret_cast<int*>(c->d_pvec + 3 * T);
+    CUDA_TRY(cudaMemsetAsync(d_rhs, 0, sizeof(double) * T, st));
+    CUDA_TRY(cudaMemcpyAsync(d_rhs, c->d_rhs, sizeof(double) * np, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    // K + sigma^2 + s^2 (arttwo.py:367-370) on top, K* (arttwo.py:373-384) below
+    AsmArgs a;
+    a.theta = c->d_theta; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
+    a.yerr = c->d_yerr; a.out = c->d_paug; a.mat_stride = (long long)(T * np); a.ld = c->npad; a.series0 = series; a.nser = 1;
+    a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1; a.use_trig = 1; a.vec2 = 1;
+    a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
+    if (launch_assemble(c, a, 1, st)) return 1;
+    a.ta = d_ts; a.tb = c->d_t; a.na = M; a.nb = c->N; a.rows_out = (int)Mpad; a.cols_out = c->npad;
+    a.out = c->d_paug + np * np; a.lower_only = 0; a.square = (M == c->N) ? 1 : 0; a.add_err = 0; a.add_jit = 0;
+    a.pad_identity = 0; a.use_trig = 0; a.kflag = nullptr;
+    if (launch_assemble(c, a, 1, st)) return 1;
+    kss_kernel<<<(M + 127) / 128, 128, 0, st>>>(c->S, c->d_theta, series, d_ts, M, d_kss);
+    LAUNCH_CHECK();
+    CholArgs g;
+    g.A = c->d_paug; g.mat_stride = (long long)(T * np); g.ld = c->npad; g.nblk = nrt; g.nmat = 1;
+    g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad; g.info = c->d_info;
+    g.A0 = c->d_paug; g.mat0 = 0;
+    g.keep_factor = 1;                          // V is read back for the row sums of squares
+    if (c->nblk > 1) {
+        g.S8 = c->d_ps8; g.rscale = d_rs; g.sgroup = sgroup; g.i8flag = d_flag;
+        i8_rowscale_kernel<<<dim3((unsigned)((T + 255) / 256), 1), 256, 0, st>>>(g, c->npad, d_kss, c->predict_test_wrap ? 0 : M);
+        LAUNCH_CHECK();
+    }
+    const bool maps_were = c->maps_valid;
+    c->maps_valid = false;                      // the tensor maps describe the batch workspace, not this matrix
+    c->group_eff = c->nblk;                     // one group: purely left-looking over the training block columns
+    const int rc = run_cholesky(c, g, st, nullptr, c->nblk, true);
+    c->maps_valid = maps_were;
+    if (rc) return 1;
+    predict_finish_kernel<<<(M + 7) / 8, 256, 0, st>>>(c->d_paug + np * np, c->npad, c->npad, M, d_rhs + np, d_ms, d_kss, c->d_theta,
+                                                       c->S.jit_off + series, d_mu, d_sd);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(wrapped, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
 static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, const double* tstar, bool have_grid,
                         double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status, void* stream) {
     if (!c || !theta || !tstar || !mean_out || !std_out) USAGE_FAIL("agpn_predict: null pointer");
@@ -918,21 +1011,7 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
     cudaStream_t st = (cudaStream_t)stream;
     const size_t np = (size_t)c->npad;
     if (ensure_batch_workspace(c, 1, 1)) return 1;
-    if ((size_t)c->nblk > c->cap_linv_blocks) {
-        cudaFree(c->d_LinvAll);
-        c->d_LinvAll = nullptr;
-        c->cap_linv_blocks = 0;
-        CUDA_TRY(cudaMalloc(&c->d_LinvAll, sizeof(double) * (size_t)c->nblk * TB * TB));
-        c->cap_linv_blocks = c->nblk;
-    }
     const size_t Mpad = ((size_t)M + TB - 1) / TB * TB;
-    if (Mpad * np > c->cap_V) {
-        cudaFree(c->d_V);
-        c->d_V = nullptr;
-        c->cap_V = 0;
-        CUDA_TRY(cudaMalloc(&c->d_V, sizeof(double) * Mpad * np));
-        c->cap_V = Mpad * np;
-    }
     if ((size_t)M > c->cap_M) {
         cudaFree(c->d_pred);
         c->d_pred = nullptr;
@@ -964,6 +1043,33 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
     m.subtract = 0; m.rflag = nullptr;
     mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
     LAUNCH_CHECK();
+    // default: K* rides along as extra block rows of the factorisation (INT8-sliced left-looking updates)
+    bool done_stacked = false;
+    if (c->i8_which == 3 && !c->predict_dmma && c->nblk <= 256) {
+        int wrapped = 0, unavailable = 0;
+        if (predict_stacked(c, series, M, Mpad, d_ts, d_ms, d_kss, d_mu, d_sd, d_kflag, st, &wrapped, &unavailable)) return 1;
+        done_stacked = !wrapped && !unavailable;
+        if (!done_stacked) {
+            CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
+            CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double), st));
+            CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 2 * c->cap_mats, st));      // info | kflag (rflag is the residual's)
+        }
+    }
+    if (!done_stacked) {
+    if ((size_t)c->nblk > c->cap_linv_blocks) {
+        cudaFree(c->d_LinvAll);
+        c->d_LinvAll = nullptr;
+        c->cap_linv_blocks = 0;
+        CUDA_TRY(cudaMalloc(&c->d_LinvAll, sizeof(double) * (size_t)c->nblk * TB * TB));
+        c->cap_linv_blocks = c->nblk;
+    }
+    if (Mpad * np > c->cap_V) {
+        cudaFree(c->d_V);
+        c->d_V = nullptr;
+        c->cap_V = 0;
+        CUDA_TRY(cudaMalloc(&c->d_V, sizeof(double) * Mpad * np));
+        c->cap_V = Mpad * np;
+    }
     // K + sigma^2 + s^2 (arttwo.py:367-370), factor (arttwo.py:371)
     AsmArgs a;
     a.theta = c->d_theta; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
@@ -986,6 +1092,8 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
     pa.z = c->d_rhs; pa.V = c->d_V; pa.mstar = d_ms; pa.kss = d_kss; pa.mean_out = d_mu; pa.std_out = d_sd;
     predict_kernel<<<(unsigned)(Mpad / TB), 256, GEMM_SMEM_BYTES, st>>>(c->S, pa);
     LAUNCH_CHECK();
+    }   // !done_stacked
+    c->last_predict_path = done_stacked ? 1 : 0;
     CUDA_TRY(cudaMemcpyAsync(mean_out, d_mu, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(std_out, d_sd, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
     int h_flags[3] = {0, 0, 0};
@@ -1188,7 +1296,7 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
         }
         g.S8 = d_s8; g.rscale = d_rs;
         tmp.group_eff = ig;
-        i8_rowscale_kernel<<<dim3((n_pad + 255) / 256, nmat), 256, 0, st>>>(g);
+        i8_rowscale_kernel<<<dim3((n_pad + 255) / 256, nmat), 256, 0, st>>>(g, n_pad, nullptr, 0);
     }
     int rc = run_cholesky(&tmp, g, st, nullptr);
     cudaError_t e = cudaStreamSynchronize(st);

@@ -56,6 +56,7 @@ struct CholArgs {
     signed char* S8 = nullptr;  // [nmat] digit planes of the current group's block columns
     int sgroup = 0;             // block columns the slice storage of one matrix holds
     int keep_factor = 0;        // 1: the FP64 panels of L are stored even when only the digit planes are read again
+    int* i8flag = nullptr;      // [nmat] or nullptr: set when a panel entry exceeds its row scale (digits would wrap)
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -70,6 +71,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 #define I8_NSL 8
 #define I8_Q (126.0 * 562949953421312.0)                         // 126 * 2^49
 #define I8_DIGIT_BIAS 0x0001020408102040ll                       // 64 * sum_{j<7} 128^j
+#define I8_QMAXF (127.0 * 562949953421312.0)                     // largest magnitude the eight digits can hold
 #define I8_TILE_BYTES (I8_NSL * TB * 32)                         // digit planes of 128 rows x 32 columns: 32 KB
 // fields (x >> sh) & 127 of two values, two digits at a time, as bytes [v0 digit a, v1 digit a, v0 digit b, v1 digit b];
 // the bias removal u - 64 (mod 256) on all four bytes at once: v = u ^ 0x40, byte = v | ((v & 0x40) << 1)
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
         if (flags & 1) {
             __syncthreads();                                       // slower warps may still read the last operand stages
             unsigned char* stg = reinterpret_cast<unsigned char*>(smem);      // [wn = 32-column chunk][slice][4096]
+            int wrapped = 0;
             const double* qmul = g.rscale + (size_t)mat * 2 * ((size_t)g.nblk * TB) + (size_t)ti * TB;
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
@@ -411,13 +414,16 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
                     unsigned piece[I8_NSL];
-                    i8_digits2(acc[mi][ni][0] * f, acc[mi][ni][1] * f, piece);
+                    const double x0 = acc[mi][ni][0] * f, x1 = acc[mi][ni][1] * f;
+                    if (fmax(fabs(x0), fabs(x1)) > I8_QMAXF) wrapped = 1;
+                    i8_digits2(x0, x1, piece);
                     unsigned char* dst = stg + wn * I8_TILE_BYTES + (wm * 4 + mi) * 256 + (ni >> 1) * 128 + (lane >> 2) * 16 +
                                          (ni & 1) * 8 + 2 * (lane & 3);
 #pragma unroll
                     for (int sl = 0; sl < I8_NSL; ++sl) *reinterpret_cast<unsigned short*>(dst + sl * (TB * 32)) = (unsigned short)piece[sl];
                 }
             }
+            if (wrapped && g.i8flag != nullptr) atomicOr(g.i8flag + mat, 1);
             __syncthreads();
             signed char* S = g.S8 + (size_t)mat * i8_slices_per_matrix(g.nblk, g.sgroup);
 #pragma unroll

@@ -47,18 +47,47 @@
 #define I8_PREFETCH 0
 #endif
 
-// ---- row scales from the diagonal of the assembled matrix: qmul = Q / r, e = r / (126 2^24) ----------------------
-// grid (n_pad / 256, nmat)
-__global__ void __launch_bounds__(256) i8_rowscale_kernel(CholArgs g) {
+// ---- row scales r_i >= max_k |L_ik|: qmul = Q / r, e = r / (126 2^24) ---------------------------------------------
+// rows i < n_sq: r_i = sqrt(K_ii) from the diagonal of the assembled matrix (sum_k L_ik^2 = K_ii);
+// rows n_sq <= i (the K* rows appended for prediction): r_i = sqrt(k**_ii) from `ext` (|K* L^-T|_i^2 <= k**_ii)
+// grid (n_rows / 256, nmat)
+__global__ void __launch_bounds__(256) i8_rowscale_kernel(CholArgs g, int n_sq, const double* __restrict__ ext, int n_ext) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     const int n = g.nblk * TB;
     if (i >= n) return;
-    const double d = g.A[(size_t)blockIdx.y * g.mat_stride + (size_t)i * g.ld + i];
+    double d = 1.0;
+    if (i < n_sq) d = g.A[(size_t)blockIdx.y * g.mat_stride + (size_t)i * g.ld + i];
+    else if (ext != nullptr && i - n_sq < n_ext) d = ext[i - n_sq];
     // a block that is not positive definite / not finite is flagged by the factorisation; its slices only have to be harmless
     const double r = (d > 0.0 && d < 1.0e300) ? sqrt(d) * (1.0 + 1.0e-9) : 1.0;
     double* rs = g.rscale + (size_t)blockIdx.y * 2 * n;
     rs[i] = I8_Q / r;
     rs[n + i] = r * (1.0 / (126.0 * 16777216.0));
+}
+
+// sum of squares of the rows of the K* L^-T block (rows row0 .., n_cols columns) and the predictive mean / std
+// (arttwo.py:388-395): mean = m(t*) + K* K^-1 r = m* - rhs_aug ; var = k** + s^2 - |K* L^-T|_row^2
+__global__ void __launch_bounds__(256) predict_finish_kernel(const double* __restrict__ V, int ld, int n_cols, int M,
+                                                             const double* __restrict__ rhs_aug, const double* __restrict__ mstar,
+                                                             const double* __restrict__ kss, const double* __restrict__ theta,
+                                                             int jit_index, double* __restrict__ mean_out, double* __restrict__ std_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= M) return;
+    const double* v = V + (size_t)row * ld;
+    double s = 0.0;
+    for (int c = 2 * lane; c < n_cols; c += 64) {
+        const double2 x = *reinterpret_cast<const double2*>(v + c);
+        s = fma(x.x, x.x, s);
+        s = fma(x.y, x.y, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const double jt = theta[jit_index];
+        mean_out[row] = mstar[row] - rhs_aug[row];
+        std_out[row] = sqrt(kss[row] + jt * jt - s);
+    }
 }
 
 // ---- slicing of block column k (rows below the diagonal block): L -> 8 int8 digit planes --------------------------

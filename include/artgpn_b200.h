@@ -193,6 +193,10 @@ int agpn_phase_ms(agpn_ctx* ctx, double* ms6, long long* launches6);
  * environment (AGPN_SYRK = dmma | i8 | i8_wide | i8_narrow).
  * agpn_slice_ms: device milliseconds / launches of the digit-slicing kernels of the last profiled call. */
 int agpn_update_path(const agpn_ctx* ctx);
+/* Path the last agpn_predict / agpn_predict_slice took: 1 = K* appended as block rows to the factorisation (INT8-sliced
+ * updates; default), 0 = stand-alone predict_kernel on the FP64 tensor instruction (AGPN_PREDICT=dmma, or the automatic
+ * fall-back when an entry of K* L^-T exceeds its row scale sqrt(k**_ii)), -1 = no prediction yet. */
+int agpn_predict_path(const agpn_ctx* ctx);
 int agpn_slice_ms(agpn_ctx* ctx, double* ms, long long* launches);
 
 #ifdef __cplusplus

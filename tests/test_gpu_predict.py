@@ -7,8 +7,20 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["stacked", "dmma"])
+def predict_path(request, monkeypatch):
+    """Default: K* rides along as extra block rows of the factorisation (INT8-sliced left-looking updates, panel
+    solves, folded forward solve); AGPN_PREDICT=dmma (read when the context is created): the stand-alone
+    predict_kernel on the FP64 tensor instruction -- also the automatic fall-back of the default path."""
+    if request.param == "dmma":
+        monkeypatch.setenv("AGPN_PREDICT", "dmma")
+    else:
+        monkeypatch.delenv("AGPN_PREDICT", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("pc", H.cases()["predict"], ids=lambda c: c["name"])
-def test_prediction_vs_reference_goldens(pc, capsys):
+def test_prediction_vs_reference_goldens(pc, capsys, predict_path):
     a = H.arrays()
     case = H.loglike_case(pc["case"])
     net = H.product_network(case)
@@ -73,3 +85,64 @@ def test_prediction_sharded_single_rank_nccl():
         dist.destroy_process_group()
     assert np.max(np.abs(mu - a["pred_G4_ds1_mean"])) <= 1e-9 * np.max(np.abs(a["pred_G4_ds1_mean"]))
     assert np.max(np.abs(sd ** 2 - a["pred_G4_ds1_std"] ** 2)) <= 1e-9 * np.max(a["pred_G4_ds1_std"] ** 2)
+
+
+def test_prediction_paths_agree_on_a_multi_block_network(monkeypatch):
+    """N = 700 (6 block columns), M = 3000: the stacked INT8 path, the DMMA predict_kernel and the oracle agree; a
+    WhiteNoise node on a grid with M == N (the reference's square-lag quirk, node.py:68-72, puts wn^2 on the
+    diagonal of K*) must still match the oracle -- the stacked path detects entries above their row scale and hands
+    over to predict_kernel."""
+    from artgpn_b200 import synth, node, weight, mean
+    from artgpn_b200.arttwo import network
+    from helpers import oracle
+    N, M = 700, 3000
+    t, y, sig = synth.make_data(N, 3, seed=2)
+    theta = synth.make_walkers(1, p=3, q=2, seed=3)
+
+    class Mm(object):
+        def __getattr__(self, name):
+            return lambda *pars: (name, list(pars))
+    m = Mm()
+    ts = np.linspace(t.min() - 3, t.max() + 3, M)
+    o_ref = synth.objects_from_row(m, m, m, theta[0], 3, 2)
+    emu, esd = oracle.prediction(t, y, sig, 2, *o_ref, ts, 2)
+    got = {}
+    for mode in ("stacked", "dmma"):
+        if mode == "dmma":
+            monkeypatch.setenv("AGPN_PREDICT", "dmma")
+        else:
+            monkeypatch.delenv("AGPN_PREDICT", raising=False)
+        net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+        nodes, ws, ms, jit = synth.objects_from_row(node, weight, mean, theta[0], 3, 2)
+        mu, sd, _ = net.prediction(nodes=nodes, weights=ws, means=ms, jitters=jit, time=ts, dataset=2)
+        assert np.max(np.abs(mu - emu)) <= 1e-9 * np.max(np.abs(emu)), mode
+        assert np.max(np.abs(sd ** 2 - esd ** 2)) <= 1e-9 * np.max(esd ** 2), mode
+        assert net.predict_path() == (1 if mode == "stacked" else 0)
+        got[mode] = (mu, sd)
+        net.close()
+    # fault injection: unit row scales for the K* rows -> entries exceed them -> detected -> predict_kernel takes over
+    monkeypatch.delenv("AGPN_PREDICT", raising=False)
+    monkeypatch.setenv("AGPN_I8_TEST_WRAP", "1")
+    net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+    nodes, ws, ms, jit = synth.objects_from_row(node, weight, mean, theta[0], 3, 2)
+    mu, sd, _ = net.prediction(nodes=nodes, weights=ws, means=ms, jitters=jit, time=ts, dataset=2)
+    assert net.predict_path() == 0
+    assert np.array_equal(mu, got["dmma"][0]) and np.array_equal(sd, got["dmma"][1])
+    net.close()
+    monkeypatch.delenv("AGPN_I8_TEST_WRAP", raising=False)
+    assert np.max(np.abs(got["stacked"][0] - got["dmma"][0])) <= 1e-11 * np.max(np.abs(emu))
+    # WhiteNoise quirk, M == N
+    monkeypatch.delenv("AGPN_PREDICT", raising=False)
+    N2 = 300
+    t2, y2, sig2 = synth.make_data(N2, 1, seed=5)
+    ts2 = t2 + 0.37
+    net = network(2, t2, y2[0], sig2[0])
+    nodes = [node.QuasiPeriodic(20.0, 25.0, 0.8), node.WhiteNoise(3.0)]
+    ws = [weight.Constant(2.0), weight.Constant(1.5)]
+    mu, sd, _ = net.prediction(nodes=nodes, weights=ws, means=[None], jitters=[0.4], time=ts2, dataset=1)
+    emu2, esd2 = oracle.prediction(t2, y2, sig2, 2, [("QuasiPeriodic", [20.0, 25.0, 0.8]), ("WhiteNoise", [3.0])],
+                                   [("Constant", [2.0]), ("Constant", [1.5])], [None], [0.4], ts2, 1)
+    assert np.max(np.abs(mu - emu2)) <= 1e-9 * np.max(np.abs(emu2))
+    ok = np.isfinite(esd2)
+    assert np.array_equal(ok, np.isfinite(sd))
+    assert np.max(np.abs(sd[ok] ** 2 - esd2[ok] ** 2)) <= 1e-9 * np.max(esd2[ok] ** 2)

@@ -1,2 +1,5 @@
-for F in 1 0; do for S in 6 8; do echo "fuse=$F streams=$S"; AGPN_I8_FUSE=$F AGPN_STREAMS=$S python tools/sweep.py 2048 128; AGPN_I8_FUSE=$F AGPN_STREAMS=$S python tools/sweep.py 2048 16; done; done
-for C in 60 66 70; do echo "clusters=$C"; AGPN_I8_CLUSTERS=$C python tools/sweep.py 2048 128; done
+python -m pytest tests/test_gpu_predict.py tests/test_gpu_robustness.py tests/test_legacy_art.py -m gpu -x -q 2>&1 | tail -5
+echo "--- stacked (default)"; python tools/predict_probe.py 1024 4000 2>&1 | tail -4
+echo "--- dmma"; AGPN_PREDICT=dmma python tools/predict_probe.py 1024 4000 2>&1 | tail -4
+echo "--- C5 stacked"; python tools/predict_probe.py 4096 100000 2>&1 | tail -3
+echo "--- C5 dmma"; AGPN_PREDICT=dmma python tools/predict_probe.py 4096 100000 2>&1 | tail -3
