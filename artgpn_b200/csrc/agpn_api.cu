@@ -107,6 +107,8 @@ struct agpn_ctx {
     int i8_which = 3;
     bool i8_persist = true;        // AGPN_I8_PERSIST=0: one CTA pair per tile instead of persistent clusters
     int i8_clusters = 74;          // persistent clusters per launch = SMs / 2
+    int i8_clusters_max = 74;
+    bool i8_clusters_fixed = false;   // AGPN_I8_CLUSTERS given
     bool fuse_slices = true;       // AGPN_I8_FUSE=0: separate i8_slice_kernel after every panel solve
     int i8_group = 8;              // group of the INT8 path: all block columns (pure left-looking) unless AGPN_GROUP is given
     signed char* d_S8 = nullptr;   // [cap_mats] digit planes of one group of block columns
@@ -244,8 +246,8 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        c->i8_clusters = sms / 2 > 0 ? sms / 2 : 1;
-        if (const char* e = getenv("AGPN_I8_CLUSTERS")) if (atoi(e) > 0) c->i8_clusters = atoi(e);
+        c->i8_clusters = c->i8_clusters_max = sms / 2 > 0 ? sms / 2 : 1;
+        if (const char* e = getenv("AGPN_I8_CLUSTERS")) if (atoi(e) > 0) { c->i8_clusters = atoi(e); c->i8_clusters_fixed = true; }
     }
     // the INT8 path is fastest purely left-looking (every C tile is visited once, measured: C3 25.1 ms with one group
     // of 16 vs 26.0 with groups of 8; C4 213 vs 249 ms); int32 accumulators bound the depth to 256 block columns
@@ -657,6 +659,14 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
     if (c->i8_which && c->d_S8 && c->nblk > 1) {
         c->group_eff = c->i8_group;
+        // small batches: a launch that takes every SM serialises the sub-batch streams (their latency-bound diagonal
+        // blocks and panel solves then wait for whole update launches); a third of the GPU per launch lets them
+        // interleave (measured, 16 walkers of 3 x 2048: 3.45 -> 3.24 ms; 128 walkers: all SMs is fastest)
+        if (!c->i8_clusters_fixed) {
+            const long long work = (long long)nmat * c->nblk;
+            c->i8_clusters = work >= 3072 ? c->i8_clusters_max : (work >= 1536 ? (2 * c->i8_clusters_max) / 3 : c->i8_clusters_max / 3);
+            if (c->i8_clusters < 1) c->i8_clusters = 1;
+        }
         // row scales r_i = sqrt(K_ii) >= |L_ik| from the assembled diagonal, before the factorisation overwrites it
         g.S8 = c->d_S8; g.rscale = c->d_rscale; g.sgroup = c->sgroup;
         PhaseScope ps(c, st, PH_SLICE, cur);
@@ -990,6 +1000,7 @@ static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, const do
     const bool maps_were = c->maps_valid;
     c->maps_valid = false;                      // the tensor maps describe the batch workspace, not this matrix
     c->group_eff = c->nblk;                     // one group: purely left-looking over the training block columns
+    if (!c->i8_clusters_fixed) c->i8_clusters = c->i8_clusters_max;      // one stream: every SM
     const int rc = run_cholesky(c, g, st, nullptr, c->nblk, true);
     c->maps_valid = maps_were;
     if (rc) return 1;

@@ -246,9 +246,11 @@ __device__ __forceinline__ void gemm_nt_prologue(const GemmPipe& p, const double
         if (c < nch) gemm_issue_chunk(p, c, Ag, lda, Bg, ldb, smem, tid);
 }
 
+// kc_limit: this warp's operand columns are exactly zero from k-chunk kc_limit on (triangular B): it skips the tensor
+// work of those chunks but still takes part in the loads and the barriers.
 __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __restrict__ Ag, int lda,
                                                  const double* __restrict__ Bg, int ldb, int K, double (&acc)[4][4][2],
-                                                 double* smem, bool active = true) {
+                                                 double* smem, bool active = true, int kc_limit = 1 << 30) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -267,7 +269,7 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __re
         if (lane == 0) mbar_arrive(p.empty + 8 * s);
 #else
         mbar_wait(p.full + 8 * s, (n / GEMM_STAGES) & 1);
-        if (active) gemm_compute_stage(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+        if (active && kc < kc_limit) gemm_compute_stage(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(p.empty + 8 * s);
         const int nxt = kc + GEMM_STAGES - 1;
@@ -278,9 +280,10 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __re
 }
 
 __device__ __forceinline__ void gemm_nt_tile(GemmPipe& p, const double* __restrict__ Ag, int lda, const double* __restrict__ Bg,
-                                             int ldb, int K, double (&acc)[4][4][2], double* smem, bool active = true) {
+                                             int ldb, int K, double (&acc)[4][4][2], double* smem, bool active = true,
+                                             int kc_limit = 1 << 30) {
     gemm_nt_prologue(p, Ag, lda, Bg, ldb, K, smem);
-    gemm_nt_mainloop(p, Ag, lda, Bg, ldb, K, acc, smem, active);
+    gemm_nt_mainloop(p, Ag, lda, Bg, ldb, K, acc, smem, active, kc_limit);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -389,7 +392,10 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        gemm_nt_tile(pipe, Aik, ld, Linv + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem);
+        // rows h * 64 + wn * 32 .. + 31 of the (lower triangular) inverse are zero right of column h * 64 + wn * 32 + 31:
+        // the wn = 0 warps stop 32 columns (two k-chunks) early
+        gemm_nt_tile(pipe, Aik, ld, Linv + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem, true,
+                     (h * BN + wn * 32 + 32) / GEMM_KC);
         // every load of this GEMM (by any thread) has completed: the in-place store is safe
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)

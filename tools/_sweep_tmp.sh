@@ -1,5 +1,2 @@
-python -m pytest tests/test_gpu_predict.py tests/test_gpu_robustness.py tests/test_legacy_art.py -m gpu -x -q 2>&1 | tail -5
-echo "--- stacked (default)"; python tools/predict_probe.py 1024 4000 2>&1 | tail -4
-echo "--- dmma"; AGPN_PREDICT=dmma python tools/predict_probe.py 1024 4000 2>&1 | tail -4
-echo "--- C5 stacked"; python tools/predict_probe.py 4096 100000 2>&1 | tail -3
-echo "--- C5 dmma"; AGPN_PREDICT=dmma python tools/predict_probe.py 4096 100000 2>&1 | tail -3
+for C in 24 37 50 74; do for S in 4 6 8; do echo -n "clusters=$C streams=$S: "; AGPN_I8_CLUSTERS=$C AGPN_STREAMS=$S python tools/sweep.py 2048 16 | cut -c40-100; done; done
+for G in 16 8 4; do echo -n "group=$G: "; AGPN_GROUP=$G python tools/sweep.py 2048 16 | cut -c40-100; done
