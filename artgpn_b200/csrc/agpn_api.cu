@@ -451,7 +451,7 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_logdet, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 3 * nmat));
-        if (c->i8_which) {
+        if (c->i8_which && c->nblk > 2) {
             c->sgroup = c->i8_group < 2 ? 2 : c->i8_group;
             CUDA_TRY(cudaMalloc(&c->d_S8, nmat * i8_slices_per_matrix(c->nblk, c->sgroup)));
             CUDA_TRY(cudaMalloc(&c->d_rscale, sizeof(double) * nmat * 2 * np));
@@ -657,7 +657,9 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     g.info = d_infoflag;
     g.A0 = c->d_A; g.mat0 = 0;
     c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
-    if (c->i8_which && c->d_S8 && c->nblk > 1) {
+    // two block columns: a single depth-128 update, where the per-tile cost of the INT8 kernel still outweighs its
+    // rate (measured at 3 x 256, 256 walkers: 0.77 vs 0.73 ms); from three block columns on it wins (3 x 384: 1.43 vs 1.45 ms)
+    if (c->i8_which && c->d_S8 && c->nblk > 2) {
         c->group_eff = c->i8_group;
         // small batches: a launch that takes every SM serialises the sub-batch streams (their latency-bound diagonal
         // blocks and panel solves then wait for whole update launches); a third of the GPU per launch lets them
@@ -795,7 +797,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t have = c->cap_mats * np * np * sizeof(double);
         const size_t per_walker = (size_t)p * ((np * np + TB * TB + 3 * np) * sizeof(double) +
-                                               (c->i8_which ? i8_slices_per_matrix(c->nblk, c->i8_group < 2 ? 2 : c->i8_group) : 0)) + 64;
+                                               ((c->i8_which && c->nblk > 2) ? i8_slices_per_matrix(c->nblk, c->i8_group < 2 ? 2 : c->i8_group) : 0)) + 64;
         const size_t fit = (size_t)((free_b + have) * 0.85) / per_walker;
         if (fit < 1) USAGE_FAIL("agpn_loglike_batch: not enough device memory for one walker");
         if (wave > fit) wave = fit;
