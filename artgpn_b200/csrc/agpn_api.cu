@@ -666,7 +666,9 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         // interleave (measured, 16 walkers of 3 x 2048: 3.45 -> 3.24 ms; 128 walkers: all SMs is fastest)
         if (!c->i8_clusters_fixed) {
             const long long work = (long long)nmat * c->nblk;
-            c->i8_clusters = work >= 3072 ? c->i8_clusters_max : (work >= 1536 ? (2 * c->i8_clusters_max) / 3 : c->i8_clusters_max / 3);
+            const bool one_stream = c->profiling || c->nsub < 2 || nmat < 2 * c->nsub;      // nothing to interleave with
+            c->i8_clusters = (one_stream || work >= 3072) ? c->i8_clusters_max
+                                                          : (work >= 1536 ? (2 * c->i8_clusters_max) / 3 : c->i8_clusters_max / 3);
             if (c->i8_clusters < 1) c->i8_clusters = 1;
         }
         // row scales r_i = sqrt(K_ii) >= |L_ik| from the assembled diagonal, before the factorisation overwrites it

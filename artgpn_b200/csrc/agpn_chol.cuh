@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
 __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0, int flags) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double zs[TB];
+    __shared__ double qs[TB];                  // Q / r_i of this row tile (digit planes)
     __shared__ double red[2][TB];
     __shared__ __align__(8) unsigned long long bars[2 * GEMM_STAGES];
     GemmPipe pipe = gemm_pipe_init(bars);
@@ -382,6 +383,7 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     if (rhs != nullptr && tid < TB) zs[tid] = rhs[(size_t)k * TB + tid];
+    if ((flags & 1) && tid >= TB) qs[tid - TB] = g.rscale[(size_t)mat * 2 * ((size_t)g.nblk * TB) + (size_t)ti * TB + tid - TB];
     __syncthreads();
     double part[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][4][2];
@@ -413,10 +415,9 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
             __syncthreads();                                       // slower warps may still read the last operand stages
             unsigned char* stg = reinterpret_cast<unsigned char*>(smem);      // [wn = 32-column chunk][slice][4096]
             int wrapped = 0;
-            const double* qmul = g.rscale + (size_t)mat * 2 * ((size_t)g.nblk * TB) + (size_t)ti * TB;
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
-                const double f = qmul[wm * 32 + mi * 8 + (lane >> 2)];
+                const double f = qs[wm * 32 + mi * 8 + (lane >> 2)];
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
                     unsigned piece[I8_NSL];
