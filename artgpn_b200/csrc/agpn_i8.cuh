@@ -177,6 +177,13 @@ __device__ __forceinline__ double i8_i2d(int v) {
     return __hiloint2double(0x43300000, (int)((unsigned)v ^ 0x80000000u)) - 4503601774854144.0;
 }
 
+// four int32 diagonals -> the double ((s0 128 + s1) 128 + s2) 128 + s3, exactly: folded in 64-bit integers (|.| < 2^47 for
+// K <= 32768) on the integer pipe, converted by adding the bits of 1.5 * 2^52 and subtracting it again (one DADD)
+__device__ __forceinline__ double i8_fold4(int s0, int s1, int s2, int s3) {
+    const long long h = (((long long)s0 * 128 + s1) * 128 + s2) * 128 + s3;
+    return __longlong_as_double(h + 0x4338000000000000ll) - 6755399441055744.0;
+}
+
 // A slice sa times B slices tb .. tb+n-1 of one K step: the schedule that covers the 36 pairs with 12 MMAs
 #define I8_MMA(sa, tb, n, first)                                                                                         \
     mma_i8(tmem + ((sa) + (tb)) * BN, i8_desc(a0 + (sa) * I8_A_BYTES), i8_desc(b0 + (tb) * I8_B_BYTES),                     \
@@ -321,12 +328,8 @@ syrk_i8_kernel(CholArgs g, int kfirst, int depth, int j0, int narrow) {
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int j = j2 + u;
-                        double H = i8_i2d(v[0][j]), Lo = i8_i2d(v[4][j]);
-#pragma unroll
-                        for (int d = 1; d < 4; ++d) {
-                            H = fma(H, 128.0, i8_i2d(v[d][j]));
-                            Lo = fma(Lo, 128.0, i8_i2d(v[4 + d][j]));
-                        }
+                        const double H = i8_fold4(v[0][j], v[1][j], v[2][j], v[3][j]);
+                        const double Lo = i8_fold4(v[4][j], v[5][j], v[6][j], v[7][j]);
                         const double val = fma(H, 268435456.0, Lo);      // H 2^28 + Lo = sum_d 128^(7-d) S_d, one rounding
                         r2[u] = (val * ei) * ecol[c8 * 8 + j];
                     }
@@ -559,12 +562,8 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             const int j = j2 + u;
-                            double H = i8_i2d(v[0][j]), Lo = i8_i2d(v[4][j]);
-#pragma unroll
-                            for (int d = 1; d < 4; ++d) {
-                                H = fma(H, 128.0, i8_i2d(v[d][j]));
-                                Lo = fma(Lo, 128.0, i8_i2d(v[4 + d][j]));
-                            }
+                            const double H = i8_fold4(v[0][j], v[1][j], v[2][j], v[3][j]);
+                            const double Lo = i8_fold4(v[4][j], v[5][j], v[6][j], v[7][j]);
                             const double val = fma(H, 268435456.0, Lo);
                             r2[u] = (val * ei) * ecol[eb][c8 * 8 + j];
                         }
