@@ -134,6 +134,11 @@ struct agpn_ctx {
     struct GraphEntry { int Ww; unsigned long long sv, wv; int exact, group, nsub, tma, mc; cudaGraphExec_t exec; long long nlaunch; };
     std::vector<GraphEntry> graphs;
     cudaEvent_t ev_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // look-ahead of the INT8 left-looking factorisation (AGPN_LOOKAHEAD=0 disables): one side stream per sub-batch stream
+    bool lookahead = true;
+    bool lookahead_forced = false;     // AGPN_LOOKAHEAD=2: for every batch size (default: few matrices only)
+    cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_la[8][2] = {};
 };
 
 // owning device allocation for the short-lived buffers of the test / API helpers (freed on every path)
@@ -278,8 +283,12 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (c->nsub < 1) c->nsub = 1;
     if (c->nsub > 8) c->nsub = 8;
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) c->nsub = 1;
+    if (const char* e = getenv("AGPN_LOOKAHEAD")) { c->lookahead = atoi(e) != 0; c->lookahead_forced = atoi(e) == 2; }
     for (int i = 0; i < c->nsub && c->nsub > 1; ++i) {
         if (cudaStreamCreateWithFlags(&c->sub[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_la[i][0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_la[i][1], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
             g_err = "agpn_create: cannot create sub-batch streams";
             agpn_destroy(c);
@@ -299,6 +308,9 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     }
     for (int i = 0; i < 8; ++i) {
         if (c->sub[i]) cudaStreamDestroy(c->sub[i]);
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->ev_la[i][0]) cudaEventDestroy(c->ev_la[i][0]);
+        if (c->ev_la[i][1]) cudaEventDestroy(c->ev_la[i][1]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -480,7 +492,11 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
 // the (narrow) update from the group's earlier columns, then its diagonal block is factorised and
 // its panel solved; after the group the whole trailing matrix takes ONE update of depth
 // 128 * group (wide).  group = 1 is the plain right-looking algorithm.
-static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor, int kstop = -1, bool no_trailing = false) {
+// look-ahead (side stream + two events, INT8 left-looking updates only): column k's diagonal tile is updated first and
+// factorised on `st` while the update of the tiles below it runs on `side`; the panel solve joins both.
+struct LookAhead { cudaStream_t side; cudaEvent_t fork, join; };
+static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor, int kstop = -1, bool no_trailing = false,
+                        const LookAhead* la = nullptr) {
     size_t local_cursor = 0;
     size_t& cur = cursor ? *cursor : local_cursor;
     // few small matrices: the left-looking narrow updates of a deep group have too few CTAs to fill the GPU
@@ -496,10 +512,20 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
         for (int k = k0; k < kend; ++k) {
             if (k > k0) {
                 PhaseScope ps(c, st, PH_SYRK, cur);
-                if ((i8 & 1) && c->i8_persist) {
+                if ((i8 & 1) && c->i8_persist && la != nullptr && g.nblk - k > 1) {
+                    CUDA_TRY(cudaEventRecord(la->fork, st));
+                    CUDA_TRY(cudaStreamWaitEvent(la->side, la->fork, 0));
+                    const int ncl_d = g.nmat < c->i8_clusters ? g.nmat : c->i8_clusters;
+                    syrk_i8_persistent_kernel<<<2 * ncl_d, I8_THREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, 1, g.nmat, 0);
+                    LAUNCH_CHECK();
+                    const int ntl = g.nblk - k - 1, total = ntl * g.nmat;
+                    const int ncl = total < c->i8_clusters ? total : c->i8_clusters;
+                    syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, la->side>>>(g, k - k0, k, 1, ntl, total, 1);
+                    CUDA_TRY(cudaEventRecord(la->join, la->side));
+                } else if ((i8 & 1) && c->i8_persist) {
                     const int ntl = g.nblk - k, total = ntl * g.nmat;
                     const int ncl = total < c->i8_clusters ? total : c->i8_clusters;
-                    syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, ntl, total);
+                    syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, ntl, total, 0);
                 } else if (i8 & 1)
                     syrk_i8_kernel<<<dim3(2 * (g.nblk - k), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
                 else if (c->maps_valid && (c->tma_which & 1))
@@ -518,6 +544,8 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
             // the panel solve writes the digit planes itself; the FP64 panel is stored only if somebody reads it
             // (a DMMA update of a mixed mode, or a caller that wants the factor: g.keep_factor)
             const int tflags = (need_slices && c->fuse_slices) ? (1 | ((i8 == 3 && !g.keep_factor) ? 2 : 0)) : 0;
+            if (k > k0 && (i8 & 1) && c->i8_persist && la != nullptr && g.nblk - k > 1)
+                CUDA_TRY(cudaStreamWaitEvent(st, la->join, 0));
             if (k < g.nblk - 1) {
                 PhaseScope ps(c, st, PH_TRSM, cur);
                 trsm_kernel<<<dim3(g.nblk - k - 1, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k, k0, tflags);
@@ -537,7 +565,7 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
             if ((i8 & 2) && c->i8_persist) {
                 const int ntl = nt * (nt + 1) / 2, total = ntl * g.nmat;
                 const int ncl = total < c->i8_clusters ? total : c->i8_clusters;
-                syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, kend - k0, kend, 0, ntl, total);
+                syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, kend - k0, kend, 0, ntl, total, 0);
             } else if (i8 & 2)
                 syrk_i8_kernel<<<dim3(nt * (nt + 1), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
             else if (c->maps_valid && (c->tma_which & 2))
@@ -700,7 +728,10 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
                 gs.rscale = g.rscale + (size_t)m0 * 2 * np;
             }
             CUDA_TRY(cudaStreamWaitEvent(c->sub[si], c->ev_fork, 0));
-            if (run_cholesky(c, gs, c->sub[si], nullptr)) return 1;
+            const LookAhead la = {c->side[si], c->ev_la[si][0], c->ev_la[si][1]};
+            // measured (3 x 2048): +4 % at 8 walkers, nothing at 16, -2 % at 128; 3 x 8192, 4 walkers: +2 %
+            const bool use_la = c->lookahead && gs.S8 && (c->lookahead_forced || nmat <= 24);
+            if (run_cholesky(c, gs, c->sub[si], nullptr, -1, false, use_la ? &la : nullptr)) return 1;
             CUDA_TRY(cudaEventRecord(c->ev_join[si], c->sub[si]));
             CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[si], 0));
         }

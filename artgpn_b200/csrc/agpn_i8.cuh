@@ -397,13 +397,13 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int* sink) {
 // ahead into the next tile's K steps while the epilogue warps drain the accumulators, the stage / phase counters run
 // on across tiles, and one extra mbarrier (`tfree`) tells the MMA thread when TMEM may be overwritten.
 //   grid.x = 2 * clusters (<= one CTA per SM), tiles of the launch: (matrix, tile) pairs, tile index fastest
-//   ntiles = tiles per matrix: narrow: nblk - j0 (tiles (j0 + t, j0)); wide: nt (nt + 1) / 2
+//   ntiles = tiles per matrix: narrow: tiles (j0 + bi0 + t, j0), t < ntiles; wide: nt (nt + 1) / 2
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
-syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles, int total) {
+syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles, int total, int bi0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2 * I8_STAGES + 3];
     __shared__ unsigned tmem_base_s;
@@ -448,7 +448,7 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
         const int t = w - mat * ntiles;
         int bi, bj;
         if (narrow) {
-            bi = t;
+            bi = t + bi0;                                           // bi0 = 1: the tiles below the diagonal tile only
             bj = 0;
         } else {
             bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);

@@ -130,6 +130,16 @@ def test_c3_update_paths_agree_and_match_oracle(monkeypatch):
         net.close()
     monkeypatch.delenv("AGPN_I8_PERSIST", raising=False)
     monkeypatch.delenv("AGPN_GROUP", raising=False)
+    # look-ahead (diagonal tile updated and factorised while a side stream updates the tiles below it): same bits
+    for la in ("2", "0"):
+        monkeypatch.setenv("AGPN_LOOKAHEAD", la)
+        net = network(2, t, y[0], sig[0], y[1], sig[1], y[2], sig[2])
+        net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], 3, 2, "Constant")[:3])
+        big = np.concatenate([theta] * 6)                    # 18 walkers = 54 matrices: the sub-batch streams are in use
+        out = net.log_likelihood_batch(big)
+        assert np.array_equal(out[:3], got[("i8", None)]) and np.array_equal(out[15:], got[("i8", None)])
+        net.close()
+    monkeypatch.delenv("AGPN_LOOKAHEAD", raising=False)
     ref = got[("dmma", None)]
     for k, v in got.items():
         assert abs(v[2] - exp) <= 1e-9 * abs(exp), (k, v[2], exp)
