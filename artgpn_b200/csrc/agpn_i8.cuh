@@ -14,7 +14,8 @@
 // The epilogue folds the 8 integer diagonals into one double (H = S_0..S_3 and Lo = S_4..S_7 are exact in a double,
 // val = H 2^28 + Lo is rounded once) and applies r_i r_j / Q^2.
 //
-// Data movement.  The slicing kernel writes the digits in the tensor core's own operand layout (UMMA canonical
+// Data movement.  The panel solve (trsm_kernel, agpn_chol.cuh; or i8_slice_kernel below with AGPN_I8_FUSE=0) writes
+// the digits in the tensor core's own operand layout (UMMA canonical
 // K-major, no swizzle: 8-row x 16-byte core matrices, LBO = 128 B, SBO = 256 B), tile by tile:
 //     slices[mat][kc32 = (column - first column of the group) / 32][row tile of 128][slice s][4096 B],
 //     in-tile (r, kb) -> (r/8) 256 + (kb/16) 128 + (r%8) 16 + kb%16
@@ -28,7 +29,10 @@
 // padded shared-memory tile before the main loop starts, folds the eight integer diagonals of that row into it
 // after the last MMA and sends the row back with one bulk store -- no thread-per-row strided global access, no
 // barrier between the epilogue threads, and the C latency hides behind the main loop.
-// Measured building blocks: tools/i8_probe.cu, profiles/r01_i8_probe_*.txt.
+// Two kernels: syrk_i8_kernel (one CTA pair per tile) and syrk_i8_persistent_kernel (default: 74 clusters walk over the
+// (matrix, tile) pairs of a launch, the producer runs ahead across tile boundaries).  The reference computes the same
+// update inside LAPACK dpotrf (scipy cho_factor, arttwo.py:284).
+// Measured building blocks: tools/i8_probe.cu, profiles/r01_i8_probe_*.txt; the product kernels: profiles/r01_i8_ncu_summary.md.
 #pragma once
 #include "agpn_chol.cuh"
 #include "agpn_tma.cuh"     // cluster helpers, mbar_expect_tx
