@@ -75,16 +75,34 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 #define I8_TILE_BYTES (I8_NSL * TB * 32)                         // digit planes of 128 rows x 32 columns: 32 KB
 // fields (x >> sh) & 127 of two values, two digits at a time, as bytes [v0 digit a, v1 digit a, v0 digit b, v1 digit b];
 // the bias removal u - 64 (mod 256) on all four bytes at once: v = u ^ 0x40, byte = v | ((v & 0x40) << 1)
-__device__ __forceinline__ unsigned i8_pack4(unsigned a0, unsigned a1, unsigned b0, unsigned b1, unsigned keep, unsigned flip, unsigned sign) {
-    const unsigned lo = __byte_perm(a0, a1, 0x0040), hi = __byte_perm(b0, b1, 0x0040);
-    const unsigned v = (__byte_perm(lo, hi, 0x5410) & keep) ^ flip;
+// (host versions of the two intrinsics so that tests/test_i8_digits_host.py can check the digit algebra without a GPU)
+__host__ __device__ __forceinline__ unsigned i8_byte_perm(unsigned a, unsigned b, unsigned sel) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, sel);
+#else
+    const unsigned long long ab = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((ab >> (8 * ((sel >> (4 * i)) & 7))) & 0xFFull) << (8 * i);
+    return r;
+#endif
+}
+__host__ __device__ __forceinline__ long long i8_rint(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2ll_rn(x);
+#else
+    return llrint(x);          // round to nearest even, like cvt.rni
+#endif
+}
+__host__ __device__ __forceinline__ unsigned i8_pack4(unsigned a0, unsigned a1, unsigned b0, unsigned b1, unsigned keep, unsigned flip, unsigned sign) {
+    const unsigned lo = i8_byte_perm(a0, a1, 0x0040), hi = i8_byte_perm(b0, b1, 0x0040);
+    const unsigned v = (i8_byte_perm(lo, hi, 0x5410) & keep) ^ flip;
     return v | ((v << 1) & sign);
 }
-__device__ __forceinline__ void i8_digits2(double x0, double x1, unsigned (&piece)[I8_NSL]) {
+__host__ __device__ __forceinline__ void i8_digits2(double x0, double x1, unsigned (&piece)[I8_NSL]) {
     // |x| <= 126 2^49 (1 + 1e-9) for every factorisable matrix (sum_k L_ik^2 = K_ii); a block that is not positive
     // definite or not finite is flagged by the factorisation and its digits only have to be harmless: NaN converts
     // to 0, overflow saturates / wraps
-    const long long q0 = __double2ll_rn(x0) + I8_DIGIT_BIAS, q1 = __double2ll_rn(x1) + I8_DIGIT_BIAS;
+    const long long q0 = i8_rint(x0) + I8_DIGIT_BIAS, q1 = i8_rint(x1) + I8_DIGIT_BIAS;
     const unsigned l0 = (unsigned)q0, l1 = (unsigned)q1;
     const unsigned h0 = (unsigned)(q0 >> 28), h1 = (unsigned)(q1 >> 28);      // digits 4 .. 7 (bits 28 .. 56 + sign)
     // slice 7 - j holds digit j (weight 128^j); words: (slice 7 | slice 6 << 16), (5 | 4), (3 | 2), (1 | 0)

@@ -34,6 +34,7 @@
 // update inside LAPACK dpotrf (scipy cho_factor, arttwo.py:284).
 // Measured building blocks: tools/i8_probe.cu, profiles/r01_i8_probe_*.txt; the product kernels: profiles/r01_i8_ncu_summary.md.
 #pragma once
+#include <cstring>
 #include "agpn_chol.cuh"
 #include "agpn_tma.cuh"     // cluster helpers, mbar_expect_tx
 
@@ -183,9 +184,16 @@ __device__ __forceinline__ double i8_i2d(int v) {
 
 // four int32 diagonals -> the double ((s0 128 + s1) 128 + s2) 128 + s3, exactly: folded in 64-bit integers (|.| < 2^47 for
 // K <= 32768) on the integer pipe, converted by adding the bits of 1.5 * 2^52 and subtracting it again (one DADD)
-__device__ __forceinline__ double i8_fold4(int s0, int s1, int s2, int s3) {
+__host__ __device__ __forceinline__ double i8_fold4(int s0, int s1, int s2, int s3) {
     const long long h = (((long long)s0 * 128 + s1) * 128 + s2) * 128 + s3;
+#ifdef __CUDA_ARCH__
     return __longlong_as_double(h + 0x4338000000000000ll) - 6755399441055744.0;
+#else
+    const long long bits = h + 0x4338000000000000ll;
+    double d;
+    memcpy(&d, &bits, sizeof(d));
+    return d - 6755399441055744.0;
+#endif
 }
 
 // A slice sa times B slices tb .. tb+n-1 of one K step: the schedule that covers the 36 pairs with 12 MMAs
