@@ -29,20 +29,29 @@ _SIGNATURES = {
     "agpn_set_exact": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "agpn_loglike_batch": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, ctypes.c_int, c_void_p,
                                           ctypes.c_int, c_void_p, c_void_p]),
+    "agpn_comm_unique_id": (ctypes.c_int, [c_void_p]),
+    "agpn_comm_init": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int]),
+    "agpn_comm_rank": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
+    "agpn_loglike_batch_sharded": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, ctypes.c_int, c_void_p,
+                                                  ctypes.c_int, c_void_p, c_void_p]),
     "agpn_covariance_block": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, c_void_p, ctypes.c_int,
                                              c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
                                              ctypes.c_int, c_void_p]),
     "agpn_mean_table": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, c_void_p]),
+    "agpn_mean_eval": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int,
+                                      c_void_p]),
     "agpn_predict": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
-    "agpn_predict_slice": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, ctypes.c_double,
-                                          ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "agpn_predict_slice": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
     "agpn_predict_cov": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, ctypes.c_double,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "agpn_kernel_eval": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p,
                                         c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p]),
     "agpn_potrf_batched": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p]),
+    "agpn_mvn_sample": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p]),
     "agpn_dmma_peak": (ctypes.c_int, [ctypes.c_int, c_void_p]),
     "agpn_i8_peak": (ctypes.c_int, [ctypes.c_int, c_void_p]),
     "agpn_launch_count": (ctypes.c_longlong, []),

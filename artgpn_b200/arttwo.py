@@ -246,30 +246,51 @@ class network(object):
                 m.pars[j] = pars.pop(0)
 
     def _mean(self, means, time=None):
-        """Mean values of every series, concatenated (arttwo.py:106-126)."""
+        """Mean values of every series, concatenated (arttwo.py:106-126).  The mean classes and parameters
+        travel with the call (agpn_mean_eval): the network's structure and cached graphs are not touched."""
         ms = list(means)
         p = self.p
-        s = Structure(p, self.q, [_node.Constant(1.0)] * self.q, [_weight.Constant(1.0)] * (p * self.q),
-                      [ms[i] if i < len(ms) else None for i in range(p)] + [None])
-        saved = self._structure
-        self._apply_structure(s)
-        theta = s.pack([_node.Constant(1.0)] * self.q, [_weight.Constant(1.0)] * (p * self.q),
-                       [ms[i] if i < len(ms) else None for i in range(p)] + [None], [0.0] * p)
-        lib = _lib.load()
-        if time is None:
-            n = np.asarray(self.time).size
-            out = np.empty((p, n))
-            _lib.check(lib.agpn_mean_table(self._ctx(), _lib.ptr(theta), None, n, _lib.ptr(out)))
-        else:
-            t = np.ascontiguousarray(time, dtype=np.float64)
-            out = np.empty((p, t.size))
-            _lib.check(lib.agpn_mean_table(self._ctx(), _lib.ptr(theta), _lib.ptr(t), t.size, _lib.ptr(out)))
-        if saved is not None:
-            self._apply_structure(saved)
+        nterms, kinds, pars = [], [], []
+        for i in range(p):
+            terms = _mean_terms(ms[i]) if i < len(ms) else []
+            nterms.append(len(terms))
+            for k, pr in terms:
+                kinds.append(k)
+                pars += pr
+        t = np.ascontiguousarray(self.time if time is None else time, dtype=np.float64)
+        out = np.empty((p, t.size))
+        nt = np.array(nterms, dtype=np.int32)
+        mk = np.array(kinds if kinds else [0], dtype=np.int32)
+        pv = np.array(pars if pars else [0.0], dtype=np.float64)
+        _lib.check(_lib.load().agpn_mean_eval(self._device, p, _lib.ptr(nt), _lib.ptr(mk), _lib.ptr(pv), _lib.ptr(t),
+                                              t.size, _lib.ptr(out)))
         return out.reshape(-1)
 
-    def sample(self, kernel, time):
-        raise NotImplementedError("network.sample is outside the likelihood / prediction path (SURVEY.md section 8)")
+    def sample(self, kernel, time, size=None, random_state=None):
+        """
+        Draw from N(0, kernel) (arttwo.py:129-147; `kernel` is a covariance MATRIX on `time`, e.g. the output of
+        _kernel_matrix / _covariance_matrix).  The reference calls scipy's multivariate_normal(..., allow_singular=True)
+        .rvs(); here the matrix is factorised on the GPU (batched Cholesky kernels, with a minimal nugget for a
+        semi-definite matrix) and the sample is L z.  The standard-normal z come from numpy on the host: the global
+        numpy state (like scipy's default), or `random_state` (seed / Generator / RandomState).  size=None -> [n].
+        """
+        K = np.ascontiguousarray(kernel, dtype=np.float64)
+        n = np.asarray(time).size
+        if K.shape != (n, n):
+            raise ValueError("kernel must be the %d x %d covariance matrix of `time`" % (n, n))
+        ns = 1 if size is None else int(size)
+        if random_state is None:
+            z = np.random.standard_normal((ns, n))
+        elif hasattr(random_state, "standard_normal"):
+            z = random_state.standard_normal((ns, n))
+        else:
+            z = np.random.default_rng(random_state).standard_normal((ns, n))
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        out = np.empty((ns, n))
+        nug = np.zeros(1)
+        _lib.check(_lib.load().agpn_mvn_sample(self._device, n, _lib.ptr(K), ns, _lib.ptr(z), _lib.ptr(out), _lib.ptr(nug)))
+        self._last_sample_nugget = float(nug[0])
+        return out[0] if size is None else out
 
     def marginalLikelihood_2ys(self, *a, **k):
         raise NotImplementedError("marginalLikelihood_2ys is outside the likelihood / prediction path")
@@ -397,8 +418,8 @@ class network(object):
         status = np.zeros(1, dtype=np.int32)
         if ts.size:
             _lib.check(_lib.load().agpn_predict_slice(self._ctx(), _lib.ptr(theta), dataset - 1, ts.size, _lib.ptr(ts),
-                                                      float(time.mean()), float(time[0]), _lib.ptr(mu), _lib.ptr(sd),
-                                                      _lib.ptr(status), None))
+                                                      time.size, int(lo), float(time.mean()), float(time[0]),
+                                                      _lib.ptr(mu), _lib.ptr(sd), _lib.ptr(status), None))
         if status[0] == STATUS_NOT_PD:
             raise np.linalg.LinAlgError("matrix is not positive definite")
         if status[0] == STATUS_NOT_FINITE:
@@ -464,11 +485,14 @@ class network(object):
         return float(ms[0]), int(n[0])
 
 
-def evaluate_mean(m, t):
-    """Value of one mean-function object on the grid t, computed on the GPU."""
+def evaluate_mean(m, t, device=None):
+    """Value of one mean-function object on the grid t, computed on the GPU (no context needed)."""
     t = np.ascontiguousarray(t, dtype=np.float64)
-    net = network(1, t, np.zeros_like(t), np.ones_like(t))
-    try:
-        return net._mean([m]).reshape(-1)
-    finally:
-        net.close()
+    terms = _mean_terms(m)
+    nt = np.array([len(terms)], dtype=np.int32)
+    mk = np.array([k for k, _ in terms] or [0], dtype=np.int32)
+    pv = np.array([x for _, pr in terms for x in pr] or [0.0], dtype=np.float64)
+    out = np.empty(t.size)
+    _lib.check(_lib.load().agpn_mean_eval(get_device() if device is None else int(device), 1, _lib.ptr(nt), _lib.ptr(mk),
+                                          _lib.ptr(pv), _lib.ptr(t), t.size, _lib.ptr(out)))
+    return out

@@ -3,6 +3,9 @@
 // launches.  No torch types; streams arrive as void*.
 #include "../../include/artgpn_b200.h"
 
+#include <dlfcn.h>
+#include <nccl.h>          // types only: the NCCL entry points are resolved with dlopen / dlsym at agpn_comm_init
+
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -21,6 +24,8 @@
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+// launches enqueued while a CUDA graph is being captured are counted here (they execute at every replay, not now)
+static thread_local long long* t_capture_launches = nullptr;
 
 #define CUDA_TRY(expr)                                                                          \
     do {                                                                                        \
@@ -40,11 +45,29 @@ static std::atomic<long long> g_launches{0};
         return 2;         \
     } while (0)
 
-#define LAUNCH_CHECK()                  \
-    do {                                \
-        g_launches.fetch_add(1);        \
-        CUDA_TRY(cudaGetLastError());   \
+#define LAUNCH_CHECK()                                        \
+    do {                                                      \
+        if (t_capture_launches) ++*t_capture_launches;        \
+        else g_launches.fetch_add(1);                         \
+        CUDA_TRY(cudaGetLastError());                         \
     } while (0)
+
+// Every entry point runs on its context's device and puts the caller's current device back on every exit path
+// (a network on cuda:1 must not silently switch the caller -- e.g. torch -- to cuda:1).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        err = cudaSetDevice(dev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ENTER_DEVICE(dev)          \
+    DeviceGuard _dev_guard(dev);   \
+    CUDA_TRY(_dev_guard.err)
 
 enum { PH_MEAN = 0, PH_ASM = 1, PH_DIAG = 2, PH_TRSM = 3, PH_SYRK = 4, PH_FINAL = 5, PH_SLICE = 6, PH_COUNT = 7 };
 
@@ -139,6 +162,12 @@ struct agpn_ctx {
     bool lookahead_forced = false;     // AGPN_LOOKAHEAD=2: for every batch size (default: few matrices only)
     cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_la[8][2] = {};
+    // walker sharding over the GPUs of one box (agpn_comm_init / agpn_loglike_batch_sharded)
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    size_t cap_gather = 0;
+    double* d_gather = nullptr;    // [nranks][slot] log-likelihoods | same for the status words (as doubles' storage: ints)
+    int* d_gstatus = nullptr;
 };
 
 // owning device allocation for the short-lived buffers of the test / API helpers (freed on every path)
@@ -228,7 +257,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) USAGE_FAIL("agpn_create: no such CUDA device");
-    CUDA_TRY(cudaSetDevice(device));
+    ENTER_DEVICE(device);
     agpn_ctx* c = new agpn_ctx();
     c->device = device;
     c->N = N;
@@ -299,9 +328,11 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     return 0;
 }
 
+static void agpn_comm_release(agpn_ctx* c);
+
 extern "C" int agpn_destroy(agpn_ctx* c) {
     if (!c) return 0;
-    cudaSetDevice(c->device);
+    DeviceGuard _dev_guard(c->device);
     for (auto& e : c->evs) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -324,6 +355,8 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_S8); cudaFree(c->d_rscale);
     cudaFree(c->d_paug); cudaFree(c->d_ps8); cudaFree(c->d_pvec);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
+    cudaFree(c->d_gather); cudaFree(c->d_gstatus);
+    agpn_comm_release(c);
     delete c;
     return 0;
 }
@@ -767,14 +800,16 @@ static int run_wave_graph(agpn_ctx* c, int Ww, const double* theta, int theta_on
                 c->graphs.erase(c->graphs.begin() + i);
             } else ++i;
         }
-        const long long l0 = g_launches.load();
+        long long captured = 0;
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(c->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
             cudaGetLastError();
             return 0;                                  // cannot capture here: the caller falls back to plain launches
         }
         size_t cur = 0;
+        t_capture_launches = &captured;
         const int rc = enqueue_wave(c, Ww, c->d_theta, c->d_out, c->gstream, cur);
+        t_capture_launches = nullptr;
         const cudaError_t ee = cudaStreamEndCapture(c->gstream, &graph);
         if (rc || ee != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
@@ -785,8 +820,7 @@ static int run_wave_graph(agpn_ctx* c, int Ww, const double* theta, int theta_on
         }
         agpn_ctx::GraphEntry ge;
         ge.Ww = Ww; ge.sv = c->struct_version; ge.wv = c->ws_version; ge.exact = c->exact; ge.group = c->group;
-        ge.nsub = c->nsub; ge.tma = tma; ge.mc = c->tma_mc; ge.exec = nullptr; ge.nlaunch = g_launches.load() - l0;
-        g_launches.store(l0);                          // captured, not executed
+        ge.nsub = c->nsub; ge.tma = tma; ge.mc = c->tma_mc; ge.exec = nullptr; ge.nlaunch = captured;
         const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) {
@@ -816,7 +850,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
     if (!c || !theta || !out) USAGE_FAIL("agpn_loglike_batch: null pointer");
     if (!c->has_structure) USAGE_FAIL("agpn_loglike_batch: call agpn_set_structure first");
     if (W < 1) USAGE_FAIL("agpn_loglike_batch: W must be >= 1");
-    CUDA_TRY(cudaSetDevice(c->device));
+    ENTER_DEVICE(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int p = c->p, D = c->S.D;
     const size_t np = (size_t)c->npad;
@@ -870,6 +904,150 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
     return 0;
 }
 
+// ---- walker sharding over NCCL -------------------------------------------------------
+// NCCL is resolved at run time (dlopen of libnccl.so.2: the copy the process has already loaded -- e.g. torch's -- is
+// reused, so ids made by either side are compatible); the library itself has no link-time NCCL dependency.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+        }
+    }
+    return api.ok ? &api : nullptr;
+}
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        ncclResult_t _r = (expr);                                                                   \
+        if (_r != ncclSuccess) {                                                                    \
+            g_err = std::string("NCCL error at ") + #expr + ": " + nccl_api()->GetErrorString(_r);  \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+static void agpn_comm_release(agpn_ctx* c) {
+    if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    c->comm = nullptr;
+    c->rank = 0;
+    c->nranks = 1;
+}
+
+extern "C" int agpn_comm_unique_id(void* id_out) {
+    if (!id_out) USAGE_FAIL("agpn_comm_unique_id: null pointer");
+    NcclApi* n = nccl_api();
+    if (!n) USAGE_FAIL("agpn_comm_unique_id: libnccl.so.2 cannot be loaded");
+    ncclUniqueId id;
+    NCCL_TRY(n->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+extern "C" int agpn_comm_init(agpn_ctx* c, const void* nccl_unique_id, int rank, int nranks) {
+    if (!c || !nccl_unique_id) USAGE_FAIL("agpn_comm_init: null pointer");
+    if (nranks < 1 || rank < 0 || rank >= nranks) USAGE_FAIL("agpn_comm_init: need 0 <= rank < nranks");
+    NcclApi* n = nccl_api();
+    if (!n) USAGE_FAIL("agpn_comm_init: libnccl.so.2 cannot be loaded");
+    ENTER_DEVICE(c->device);
+    agpn_comm_release(c);
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, sizeof(id));
+    NCCL_TRY(n->CommInitRank(&c->comm, nranks, id, rank));
+    c->rank = rank;
+    c->nranks = nranks;
+    return 0;
+}
+
+extern "C" int agpn_comm_rank(const agpn_ctx* c, int* rank, int* nranks) {
+    if (!c) USAGE_FAIL("agpn_comm_rank: null context");
+    if (rank) *rank = c->rank;
+    if (nranks) *nranks = c->nranks;
+    return 0;
+}
+
+// rows [lo, hi) of rank r: contiguous blocks, the first W % nranks ranks get one more
+static void shard_bounds(int W, int nranks, int r, int* lo, int* hi) {
+    const int base = W / nranks, rem = W % nranks;
+    *lo = r * base + (r < rem ? r : rem);
+    *hi = *lo + base + (r < rem ? 1 : 0);
+}
+
+// gathered [nranks][slot] -> contiguous [W] (uneven shards leave holes at the end of the short ranks' slots)
+__global__ void shard_compact_kernel(const double* g, const int* gs, int W, int nranks, int slot, double* out, int* status) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const int base = W / nranks, rem = W % nranks;
+    int r = (base + 1) * rem > w ? w / (base + 1) : rem + (base > 0 ? (w - (base + 1) * rem) / base : 0);
+    const int lo = r * base + (r < rem ? r : rem);
+    out[w] = g[(size_t)r * slot + (w - lo)];
+    if (status) status[w] = gs[(size_t)r * slot + (w - lo)];
+}
+
+extern "C" int agpn_loglike_batch_sharded(agpn_ctx* c, int W, const double* theta, int theta_on_device, double* out,
+                                          int out_on_device, int* status, void* stream) {
+    if (!c || !theta || !out) USAGE_FAIL("agpn_loglike_batch_sharded: null pointer");
+    if (!c->has_structure) USAGE_FAIL("agpn_loglike_batch_sharded: call agpn_set_structure first");
+    if (!c->comm) USAGE_FAIL("agpn_loglike_batch_sharded: call agpn_comm_init first");
+    if (W < 1) USAGE_FAIL("agpn_loglike_batch_sharded: W must be >= 1");
+    NcclApi* n = nccl_api();
+    ENTER_DEVICE(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int lo, hi;
+    shard_bounds(W, c->nranks, c->rank, &lo, &hi);
+    const int slot = (W + c->nranks - 1) / c->nranks;
+    const size_t need = (size_t)slot * c->nranks + (size_t)W;
+    if (need > c->cap_gather) {
+        cudaFree(c->d_gather); cudaFree(c->d_gstatus);
+        c->d_gather = nullptr; c->d_gstatus = nullptr; c->cap_gather = 0;
+        CUDA_TRY(cudaMalloc(&c->d_gather, sizeof(double) * need));
+        CUDA_TRY(cudaMalloc(&c->d_gstatus, sizeof(int) * need));
+        c->cap_gather = need;
+    }
+    double* mine = c->d_gather + (size_t)c->rank * slot;          // the likelihood kernels write straight into the send slot
+    int* mine_s = c->d_gstatus + (size_t)c->rank * slot;
+    if (hi > lo) {
+        std::vector<int> hs(status ? hi - lo : 0);                 // a batch may run in several waves: statuses come back per call
+        const int rc = agpn_loglike_batch(c, hi - lo, theta + (size_t)lo * c->S.D, theta_on_device, mine, 1,
+                                          status ? hs.data() : nullptr, stream);
+        if (rc) return rc;
+        if (status) CUDA_TRY(cudaMemcpy(mine_s, hs.data(), sizeof(int) * (hi - lo), cudaMemcpyHostToDevice));
+    }
+    NCCL_TRY(n->AllGather(mine, c->d_gather, (size_t)slot, ncclDouble, c->comm, st));
+    if (status) NCCL_TRY(n->AllGather(mine_s, c->d_gstatus, (size_t)slot, ncclInt32, c->comm, st));
+    double* d_full = c->d_gather + (size_t)slot * c->nranks;
+    int* d_fulls = c->d_gstatus + (size_t)slot * c->nranks;
+    const bool even = (W % c->nranks) == 0;
+    const double* src = c->d_gather;
+    const int* srcs = c->d_gstatus;
+    if (!even) {
+        shard_compact_kernel<<<(W + 255) / 256, 256, 0, st>>>(c->d_gather, c->d_gstatus, W, c->nranks, slot, d_full,
+                                                             status ? d_fulls : nullptr);
+        LAUNCH_CHECK();
+        src = d_full;
+        srcs = d_fulls;
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, src, sizeof(double) * W, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, srcs, sizeof(int) * W, cudaMemcpyDeviceToHost, st));
+    if (!out_on_device || status) CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int agpn_covariance_block(agpn_ctx* c, const double* theta, int series, const double* ta, int na,
                                      const double* tb, int nb, int square_quirk, int add_errors, double* out,
                                      int out_on_device, void* stream) {
@@ -880,7 +1058,7 @@ extern "C" int agpn_covariance_block(agpn_ctx* c, const double* theta, int serie
     if (!tb) nb = c->N;
     if (na < 1 || nb < 1) USAGE_FAIL("agpn_covariance_block: empty grid");
     if (add_errors && (na != c->N || nb != c->N)) USAGE_FAIL("agpn_covariance_block: add_errors needs the training grid size");
-    CUDA_TRY(cudaSetDevice(c->device));
+    ENTER_DEVICE(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     double *d_th = nullptr, *d_ta = nullptr, *d_tb = nullptr, *d_out = nullptr;
     int rc = 0;
@@ -931,7 +1109,7 @@ extern "C" int agpn_mean_table(agpn_ctx* c, const double* theta, const double* t
     if (!c->has_structure) USAGE_FAIL("agpn_mean_table: call agpn_set_structure first");
     if (!t) n = c->N;
     if (n < 1) USAGE_FAIL("agpn_mean_table: empty grid");
-    CUDA_TRY(cudaSetDevice(c->device));
+    ENTER_DEVICE(c->device);
     DevBuf b_th, b_t, b_o;
     CUDA_TRY(b_th.alloc(c->S.D));
     CUDA_TRY(b_o.alloc((size_t)c->p * n));
@@ -953,18 +1131,64 @@ extern "C" int agpn_mean_table(agpn_ctx* c, const double* theta, const double* t
     return 0;
 }
 
+// mean functions on a grid without a context: the kinds / parameters travel with the call, so neither a context's
+// structure nor its cached CUDA graphs are touched (network._mean, MeanModel.__call__)
+extern "C" int agpn_mean_eval(int device, int p, const int* mean_nterms, const int* mean_kind, const double* pars,
+                              const double* t, int n, double* out) {
+    if (!mean_nterms || !t || !out) USAGE_FAIL("agpn_mean_eval: null pointer");
+    if (p < 1 || p > AGPN_MAXP) USAGE_FAIL("agpn_mean_eval: need 1 <= p <= 8 series");
+    if (n < 1) USAGE_FAIL("agpn_mean_eval: empty grid");
+    Structure S;
+    memset(&S, 0, sizeof(S));
+    S.p = p; S.q = 1; S.use_means = 1;
+    int nt = 0, off = 0;
+    for (int i = 0; i < p; ++i) {
+        S.mean_first[i] = nt;
+        for (int u = 0; u < mean_nterms[i]; ++u) {
+            if (nt >= AGPN_MAXTERMS) USAGE_FAIL("agpn_mean_eval: more than 32 mean terms");
+            if (!mean_kind || !pars) USAGE_FAIL("agpn_mean_eval: null pointer");
+            const int np_ = mean_npars(mean_kind[nt]);
+            if (np_ < 0) USAGE_FAIL("agpn_mean_eval: unknown mean kind");
+            S.mean_kind[nt] = mean_kind[nt];
+            S.mean_off[nt] = off;
+            off += np_;
+            ++nt;
+        }
+    }
+    S.mean_first[p] = nt;
+    S.jit_off = off;
+    S.D = off > 0 ? off : 1;
+    ENTER_DEVICE(device);
+    DevBuf b_th, b_t, b_o;
+    CUDA_TRY(b_th.alloc(S.D));
+    CUDA_TRY(b_t.alloc(n));
+    CUDA_TRY(b_o.alloc((size_t)p * n));
+    if (off > 0) CUDA_TRY(cudaMemcpy(b_th.p, pars, sizeof(double) * off, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b_t.p, t, sizeof(double) * n, cudaMemcpyHostToDevice));
+    MeanArgs m;
+    m.theta = b_th.p; m.t = b_t.p; m.n = n; m.n_pad = n; m.tmean = host_mean(t, n); m.t0 = t[0]; m.y = nullptr; m.out = b_o.p;
+    m.series0 = 0; m.nser = p; m.subtract = 0; m.rflag = nullptr;
+    mean_kernel<<<dim3(p, 1), 256>>>(S, m);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpy(out, b_o.p, sizeof(double) * (size_t)p * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, const double* tstar, bool have_grid,
-                        double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status, void* stream);
+                        int grid_M, int grid_off, double grid_mean, double grid_t0, double* mean_out, double* std_out,
+                        int* status, void* stream);
 
 extern "C" int agpn_predict(agpn_ctx* c, const double* theta, int series, int M, const double* tstar,
                             double* mean_out, double* std_out, int* status, void* stream) {
-    return predict_impl(c, theta, series, M, tstar, false, 0.0, 0.0, mean_out, std_out, status, stream);
+    return predict_impl(c, theta, series, M, tstar, false, M, 0, 0.0, 0.0, mean_out, std_out, status, stream);
 }
 
 extern "C" int agpn_predict_slice(agpn_ctx* c, const double* theta, int series, int M, const double* tstar,
-                                  double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status,
-                                  void* stream) {
-    return predict_impl(c, theta, series, M, tstar, true, grid_mean, grid_t0, mean_out, std_out, status, stream);
+                                  int grid_M, int grid_offset, double grid_mean, double grid_t0, double* mean_out,
+                                  double* std_out, int* status, void* stream) {
+    if (grid_offset < 0 || grid_M < M || grid_offset > grid_M - M) USAGE_FAIL("agpn_predict_slice: slice outside the grid");
+    return predict_impl(c, theta, series, M, tstar, true, grid_M, grid_offset, grid_mean, grid_t0, mean_out, std_out, status,
+                        stream);
 }
 
 // Prediction on the factorisation kernels.  V = K* L^-T is what the blocked Cholesky computes for block rows appended
@@ -973,8 +1197,9 @@ extern "C" int agpn_predict_slice(agpn_ctx* c, const double* theta, int series, 
 // panel solves, the folded forward solve leaves -K* K^-1 r in the appended part of the right-hand side, and one pass
 // over V gives the row sums of squares (arttwo.py:371-395).  *wrapped: an entry exceeded its row scale (a covariance
 // that is not positive semi-definite jointly, e.g. the WhiteNoise square-lag quirk) -> the caller uses predict_kernel.
-static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, const double* d_ts, const double* d_ms, double* d_kss,
-                           double* d_mu, double* d_sd, int* d_kflag, cudaStream_t st, int* wrapped, int* unavailable) {
+static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, int grid_M, int grid_off, const double* d_ts,
+                           const double* d_ms, double* d_kss, double* d_mu, double* d_sd, int* d_kflag, cudaStream_t st,
+                           int* wrapped, int* unavailable) {
     const size_t np = (size_t)c->npad;
     const size_t T = np + Mpad;
     const int nrt = (int)(T / TB);
@@ -1017,7 +1242,9 @@ static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, const do
     a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
     if (launch_assemble(c, a, 1, st)) return 1;
     a.ta = d_ts; a.tb = c->d_t; a.na = M; a.nb = c->N; a.rows_out = (int)Mpad; a.cols_out = c->npad;
-    a.out = c->d_paug + np * np; a.lower_only = 0; a.square = (M == c->N) ? 1 : 0; a.add_err = 0; a.add_jit = 0;
+    // WhiteNoise's square-lag quirk (node.py:68-72) looks at the WHOLE prediction grid: wn^2 where the grid has N points
+    // and (index in the grid) == (training index), whatever slice of it this call evaluates
+    a.out = c->d_paug + np * np; a.lower_only = 0; a.square = (grid_M == c->N) ? 1 : 0; a.row_off = grid_off; a.add_err = 0; a.add_jit = 0;
     a.pad_identity = 0; a.use_trig = 0; a.kflag = nullptr;
     if (launch_assemble(c, a, 1, st)) return 1;
     kss_kernel<<<(M + 127) / 128, 128, 0, st>>>(c->S, c->d_theta, series, d_ts, M, d_kss);
@@ -1048,12 +1275,13 @@ static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, const do
 }
 
 static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, const double* tstar, bool have_grid,
-                        double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status, void* stream) {
+                        int grid_M, int grid_off, double grid_mean, double grid_t0, double* mean_out, double* std_out,
+                        int* status, void* stream) {
     if (!c || !theta || !tstar || !mean_out || !std_out) USAGE_FAIL("agpn_predict: null pointer");
     if (!c->has_structure) USAGE_FAIL("agpn_predict: call agpn_set_structure first");
     if (series < 0 || series >= c->p) USAGE_FAIL("agpn_predict: series out of range");
     if (M < 1) USAGE_FAIL("agpn_predict: empty prediction grid");
-    CUDA_TRY(cudaSetDevice(c->device));
+    ENTER_DEVICE(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t np = (size_t)c->npad;
     if (ensure_batch_workspace(c, 1, 1)) return 1;
@@ -1093,7 +1321,7 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
     bool done_stacked = false;
     if (c->i8_which == 3 && !c->predict_dmma && c->nblk <= 256) {
         int wrapped = 0, unavailable = 0;
-        if (predict_stacked(c, series, M, Mpad, d_ts, d_ms, d_kss, d_mu, d_sd, d_kflag, st, &wrapped, &unavailable)) return 1;
+        if (predict_stacked(c, series, M, Mpad, grid_M, grid_off, d_ts, d_ms, d_kss, d_mu, d_sd, d_kflag, st, &wrapped, &unavailable)) return 1;
         done_stacked = !wrapped && !unavailable;
         if (!done_stacked) {
             CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
@@ -1134,7 +1362,7 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
     LAUNCH_CHECK();
     PredArgs pa;
     pa.theta = c->d_theta; pa.tstar = d_ts; pa.ttrain = c->d_t; pa.M = M; pa.N = c->N; pa.n_pad = c->npad; pa.nblk = c->nblk;
-    pa.series = series; pa.square = (M == c->N) ? 1 : 0; pa.exact = c->exact ? 1 : 0; pa.L = c->d_A; pa.ld = c->npad; pa.Linv = c->d_LinvAll;
+    pa.series = series; pa.square = (grid_M == c->N) ? 1 : 0; pa.row_off = grid_off; pa.exact = c->exact ? 1 : 0; pa.L = c->d_A; pa.ld = c->npad; pa.Linv = c->d_LinvAll;
     pa.z = c->d_rhs; pa.V = c->d_V; pa.mstar = d_ms; pa.kss = d_kss; pa.mean_out = d_mu; pa.std_out = d_sd;
     predict_kernel<<<(unsigned)(Mpad / TB), 256, GEMM_SMEM_BYTES, st>>>(c->S, pa);
     LAUNCH_CHECK();
@@ -1169,7 +1397,7 @@ extern "C" int agpn_predict_cov(agpn_ctx* c, const double* theta, int series, in
     if (!c->has_structure) USAGE_FAIL("agpn_predict_cov: call agpn_set_structure first");
     if (series < 0 || series >= c->p) USAGE_FAIL("agpn_predict_cov: series out of range");
     if (M < 1) USAGE_FAIL("agpn_predict_cov: empty prediction grid");
-    CUDA_TRY(cudaSetDevice(c->device));
+    ENTER_DEVICE(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int D = c->S.D;
     const size_t npad = (size_t)c->npad;
@@ -1276,7 +1504,7 @@ extern "C" int agpn_kernel_eval(int device, int family, int kind, const double* 
     const bool nonstat = (kind == K_LINEAR || kind == K_POLY);
     if (nonstat && (!t1 || !t2)) USAGE_FAIL("agpn_kernel_eval: Linear / Polynomial need t1 and t2");
     if (!nonstat && !r) USAGE_FAIL("agpn_kernel_eval: stationary kernels need r");
-    CUDA_TRY(cudaSetDevice(device));
+    ENTER_DEVICE(device);
     const size_t n = (size_t)rows * cols;
     DevBuf b_r, b_t1, b_t2, b_o;
     CUDA_TRY(b_o.alloc(n));
@@ -1306,14 +1534,16 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     if (rhs && !quad) USAGE_FAIL("agpn_potrf_batched: rhs needs quad");
     if (n_pad < TB || n_pad % TB) USAGE_FAIL("agpn_potrf_batched: n_pad must be a positive multiple of 128");
     if (nmat < 1 || nmat > 65535) USAGE_FAIL("agpn_potrf_batched: 1 <= nmat <= 65535");
-    CUDA_TRY(cudaSetDevice(device));
+    ENTER_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
     agpn_ctx tmp;
     tmp.device = device;
     if (const char* e = getenv("AGPN_GROUP")) { tmp.group = atoi(e) > 0 ? atoi(e) : 8; tmp.group_fixed = true; }
     if (set_kernel_attrs(&tmp)) return 1;
-    double* d_linv = nullptr;
-    CUDA_TRY(cudaMalloc(&d_linv, sizeof(double) * (size_t)nmat * TB * TB));
+    DevBuf b_linv, b_rs;
+    struct ByteBuf { signed char* p = nullptr; ~ByteBuf() { if (p) cudaFree(p); } } b_s8;
+    CUDA_TRY(b_linv.alloc((size_t)nmat * TB * TB));
+    double* d_linv = b_linv.p;
     CUDA_TRY(cudaMemsetAsync(logdet, 0, sizeof(double) * nmat, st));
     if (quad) CUDA_TRY(cudaMemsetAsync(quad, 0, sizeof(double) * nmat, st));
     CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int) * nmat, st));
@@ -1328,36 +1558,94 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     if (const char* e = getenv("AGPN_I8_FUSE")) tmp.fuse_slices = atoi(e) != 0;
     if (const char* e = getenv("AGPN_I8_PERSIST")) tmp.i8_persist = atoi(e) != 0;
     g.keep_factor = 1;                                   // the caller reads L
-    signed char* d_s8 = nullptr;
-    double* d_rs = nullptr;
     if (tmp.i8_which && g.nblk > 1) {
         int ig = tmp.group_fixed ? tmp.group : g.nblk;
         if (ig > 256) ig = 256;
         g.sgroup = ig < 2 ? 2 : ig;
-        if (cudaMalloc(&d_s8, (size_t)nmat * i8_slices_per_matrix(g.nblk, g.sgroup)) != cudaSuccess ||
-            cudaMalloc(&d_rs, sizeof(double) * (size_t)nmat * 2 * n_pad) != cudaSuccess) {
+        if (cudaMalloc(&b_s8.p, (size_t)nmat * i8_slices_per_matrix(g.nblk, g.sgroup)) != cudaSuccess ||
+            b_rs.alloc((size_t)nmat * 2 * n_pad) != cudaSuccess) {
             cudaGetLastError();
-            cudaFree(d_s8); cudaFree(d_rs); cudaFree(d_linv);
             USAGE_FAIL("agpn_potrf_batched: not enough device memory for the digit planes");
         }
-        g.S8 = d_s8; g.rscale = d_rs;
+        g.S8 = b_s8.p; g.rscale = b_rs.p;
         tmp.group_eff = ig;
         i8_rowscale_kernel<<<dim3((n_pad + 255) / 256, nmat), 256, 0, st>>>(g, n_pad, nullptr, 0);
+        LAUNCH_CHECK();
     }
-    int rc = run_cholesky(&tmp, g, st, nullptr);
-    cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(d_linv);
-    cudaFree(d_s8);
-    cudaFree(d_rs);
+    const int rc = run_cholesky(&tmp, g, st, nullptr);
+    const cudaError_t e = cudaStreamSynchronize(st);       // the temporaries are freed (RAII) only after the work has drained
     if (rc) return rc;
     CUDA_TRY(e);
+    return 0;
+}
+
+// ---- draws from N(0, K) (network.sample, arttwo.py:129-147) ---------------------------------------------------------
+// A[npad][npad] = K + nugget I on [n][n], identity padding
+__global__ void sample_pad_kernel(const double* __restrict__ K, int n, int npad, double nugget, double* __restrict__ A) {
+    const size_t total = (size_t)npad * npad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / npad), j = (int)(idx % npad);
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < n && j < n) v = K[(size_t)i * n + j] + ((i == j) ? nugget : 0.0);
+        A[idx] = v;
+    }
+}
+// out[s][i] = sum_{j <= i} L[i][j] z[s][j]; grid (n, ceil(nsamp / 8)), one warp per (row, sample)
+__global__ void __launch_bounds__(256) sample_trmv_kernel(const double* __restrict__ L, int ld, int n, const double* __restrict__ z,
+                                                          int nsamp, double* __restrict__ out) {
+    const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sidx = blockIdx.y * 8 + warp;
+    if (sidx >= nsamp) return;
+    const double* lr = L + (size_t)i * ld;
+    const double* zr = z + (size_t)sidx * n;
+    double acc = 0.0;
+    for (int j = lane; j <= i; j += 32) acc = fma(lr[j], zr[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(size_t)sidx * n + i] = acc;
+}
+
+extern "C" int agpn_mvn_sample(int device, int n, const double* K, int nsamp, const double* z, double* out,
+                               double* nugget_used) {
+    if (!K || !z || !out) USAGE_FAIL("agpn_mvn_sample: null pointer");
+    if (n < 1 || nsamp < 1) USAGE_FAIL("agpn_mvn_sample: need n >= 1 and nsamp >= 1");
+    ENTER_DEVICE(device);
+    const int npad = (n + TB - 1) / TB * TB;
+    DevBuf b_K, b_A, b_z, b_o, b_ld;
+    struct IntBuf { int* p = nullptr; ~IntBuf() { if (p) cudaFree(p); } } b_info;
+    CUDA_TRY(b_K.alloc((size_t)n * n));
+    CUDA_TRY(b_A.alloc((size_t)npad * npad));
+    CUDA_TRY(b_z.alloc((size_t)n * nsamp));
+    CUDA_TRY(b_o.alloc((size_t)n * nsamp));
+    CUDA_TRY(b_ld.alloc(1));
+    CUDA_TRY(cudaMalloc(&b_info.p, sizeof(int)));
+    CUDA_TRY(cudaMemcpy(b_K.p, K, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b_z.p, z, sizeof(double) * (size_t)n * nsamp, cudaMemcpyHostToDevice));
+    double dmax = 0.0;
+    for (int i = 0; i < n; ++i) dmax = std::max(dmax, std::fabs(K[(size_t)i * n + i]));
+    if (!(dmax > 0.0) || !std::isfinite(dmax)) dmax = 1.0;
+    // allow_singular semantics: a semi-definite K gets the smallest diagonal shift that makes it factorisable
+    double nugget = 0.0;
+    int info = 1;
+    for (int attempt = 0; attempt < 6 && info; ++attempt) {      // nugget <= 1e-6 max|K_ii|: beyond that K is not PSD
+        sample_pad_kernel<<<1024, 256>>>(b_K.p, n, npad, nugget, b_A.p);
+        LAUNCH_CHECK();
+        if (agpn_potrf_batched(device, 1, npad, b_A.p, nullptr, b_ld.p, nullptr, b_info.p, nullptr)) return 1;
+        CUDA_TRY(cudaMemcpy(&info, b_info.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (info) nugget = (nugget == 0.0) ? 1e-14 * dmax : nugget * 100.0;
+    }
+    if (info) USAGE_FAIL("agpn_mvn_sample: covariance is not positive semi-definite");
+    sample_trmv_kernel<<<dim3(n, (nsamp + 7) / 8), 256>>>(b_A.p, npad, n, b_z.p, nsamp, b_o.p);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpy(out, b_o.p, sizeof(double) * (size_t)n * nsamp, cudaMemcpyDeviceToHost));
+    if (nugget_used) *nugget_used = nugget;
     return 0;
 }
 
 // ---- INT8 tensor-path peak probe (roofline denominator of syrk_i8_kernel) --------------------
 extern "C" int agpn_i8_peak(int device, double* tops) {
     if (!tops) USAGE_FAIL("agpn_i8_peak: null pointer");
-    CUDA_TRY(cudaSetDevice(device));
+    ENTER_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     const int grid = prop.multiProcessorCount, iters = 40000;
@@ -1403,7 +1691,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
 
 extern "C" int agpn_dmma_peak(int device, double* tflops) {
     if (!tflops) USAGE_FAIL("agpn_dmma_peak: null pointer");
-    CUDA_TRY(cudaSetDevice(device));
+    ENTER_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     const int grid = prop.multiProcessorCount * 2, threads = 256, iters = 20000;

@@ -28,6 +28,7 @@ struct AsmArgs {
     int series0, nser;
     int lower_only;          // tiles enumerated over the lower block triangle (square grids)
     int square;              // WhiteNoise quirk: lag array is square
+    int row_off = 0;         // rows are a slice of a larger (square) grid: the quirk's diagonal is row + row_off == column
     int add_err;             // + yerr^2 on the diagonal
     int add_jit;             // + jitter^2 on the diagonal
     int pad_identity;        // entries outside [na][nb]: 1 on the diagonal, else 0
@@ -116,14 +117,14 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
         for (int j = 0; j < q; ++j) {
             const int slot = s_slot[j];
             if (slot < 0) continue;
-            const double b = s_node[j].b;
+            const double per = s_node[j].per;
             double sv, cv;
             if (tid < ASM_TILE) {
-                sincos(b * (s_ta[tid] - g.torigin), &sv, &cv);
+                phase_sincos(s_ta[tid] - g.torigin, per, &sv, &cv);
                 s_trig[slot][0][tid] = sv;
                 s_trig[slot][1][tid] = cv;
             } else {
-                sincos(b * (s_tb[tid - ASM_TILE] - g.torigin), &sv, &cv);
+                phase_sincos(s_tb[tid - ASM_TILE] - g.torigin, per, &sv, &cv);
                 s_trig[slot][2][tid - ASM_TILE] = sv;
                 s_trig[slot][3][tid - ASM_TILE] = cv;
             }
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
         if (gi >= g.rows_out) break;
         const double t1 = s_ta[row];
         const double r0 = t1 - tb0, r1 = t1 - tb1;
-        const bool dg0 = g.square && (gi == gj0), dg1 = g.square && (gi == gj0 + 1);
+        const bool dg0 = g.square && (gi + g.row_off == gj0), dg1 = g.square && (gi + g.row_off == gj0 + 1);
         double F0[AGPN_MAXQ], F1[AGPN_MAXQ];
 #pragma unroll
         for (int j = 0; j < AGPN_MAXQ; ++j) {
@@ -312,7 +313,7 @@ __device__ __forceinline__ void asm_fast_rows(const AsmArgs& g, int q, int w, in
 template <int P, bool WSE>
 __global__ void __launch_bounds__(256, 2) assemble_fast_kernel(const __grid_constant__ Structure S, const AsmArgs g) {
     __shared__ double s_a[ASMF_MAXQ][2];                       // a_j, c_j
-    __shared__ double s_b[ASMF_MAXQ];                          // pi / P_j (0: no sine term)
+    __shared__ double s_b[ASMF_MAXQ];                          // P_j (0: no sine term)
     __shared__ double s_amp[AGPN_MAXP][ASMF_MAXQ];             // w_ij^2
     __shared__ double s_cs[AGPN_MAXP][ASMF_MAXQ];              // c_j + cw_ij
     __shared__ double s_ta[ASM_TILE], s_tb[ASM_TILE];
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(256, 2) assemble_fast_kernel(const __grid_cons
         const PKern k = prep_kernel(0, S.node_kind[tid], th + S.node_off[tid]);
         s_a[tid][0] = (k.kind == K_SE) ? 0.0 : k.a;
         s_a[tid][1] = (k.kind == K_SE) ? k.a : k.c;            // SE keeps its -1/(2 ell^2) in .a
-        s_b[tid] = (k.kind == K_SE) ? 0.0 : k.b;
+        s_b[tid] = (k.kind == K_SE) ? 0.0 : k.per;
     }
     __syncthreads();
     if (tid >= 32 && tid < 32 + P * q) {
@@ -368,14 +369,15 @@ __global__ void __launch_bounds__(256, 2) assemble_fast_kernel(const __grid_cons
     }
     __syncthreads();
     for (int j = 0; j < q; ++j) {
-        const double b = s_b[j];
-        double sv, cv;
+        const double per = s_b[j];
+        const bool nosin = S.node_kind[j] == K_SE;
+        double sv = 0.0, cv = 1.0;
         if (tid < ASM_TILE) {
-            sincos(b * (s_ta[tid] - g.torigin), &sv, &cv);
+            if (!nosin) phase_sincos(s_ta[tid] - g.torigin, per, &sv, &cv);
             s_rowt[j][0][tid] = sv;
             s_rowt[j][1][tid] = cv;
         } else {
-            sincos(b * (s_tb[tid - ASM_TILE] - g.torigin), &sv, &cv);
+            if (!nosin) phase_sincos(s_tb[tid - ASM_TILE] - g.torigin, per, &sv, &cv);
             s_colt[j][0][tid - ASM_TILE] = sv;
             s_colt[j][1][tid - ASM_TILE] = cv;
         }

@@ -54,6 +54,7 @@ struct PKern {
     int family;     // 0 node, 1 weight (RQP differs, node.py:186-189 vs weight.py:420-423)
     double amp;
     double a, b, c, d;
+    double per;     // the period P itself for kernels with a sin(pi |r| / P) term (phase-reduced tables), else 0
 };
 
 #define AGPN_PI 3.141592653589793238462643383279502884
@@ -64,6 +65,7 @@ __host__ __device__ inline PKern prep_kernel(int family, int kind, const double*
     k.family = family;
     k.amp = 1.0;
     k.a = k.b = k.c = k.d = 0.0;
+    k.per = 0.0;
     const double* h = pars;
     if (family == 1 && kind != K_CONSTANT && kind != K_WHITENOISE) {
         k.amp = pars[0] * pars[0];          // weight**2 (weight.py:141 etc.)
@@ -81,11 +83,13 @@ __host__ __device__ inline PKern prep_kernel(int family, int kind, const double*
             break;
         case K_PERIODIC:                    // exp(-2 sin^2(pi|r|/P)/ell^2), pars (P, ell)
             k.b = AGPN_PI / h[0];
+            k.per = h[0];
             k.a = -2.0 / (h[1] * h[1]);
             break;
         case K_QP:                          // pars (ell_e, P, ell_p)
             k.c = -1.0 / (2.0 * h[0] * h[0]);
             k.b = AGPN_PI / h[1];
+            k.per = h[1];
             k.a = -2.0 / (h[2] * h[2]);
             break;
         case K_RQ:                          // 1/(1 + r^2/(2 alpha ell^2))^alpha, pars (alpha, ell)
@@ -96,6 +100,7 @@ __host__ __device__ inline PKern prep_kernel(int family, int kind, const double*
             k.d = h[0];
             k.c = 1.0 / (2.0 * h[0] * h[1] * h[1]);
             k.b = AGPN_PI / h[2];
+            k.per = h[2];
             k.a = -2.0 / (h[3] * h[3]);
             break;
         case K_COSINE:                      // cos(2 pi |r| / P)
@@ -136,6 +141,20 @@ __host__ __device__ inline bool kernel_has_sin(int kind) {
 }
 
 #ifdef __CUDACC__
+// sin and cos of pi dt / P for the angle-addition tables, without losing the phase to the size of the argument
+// (dt / P reaches hundreds of periods: a plain sincos(b * dt) carries eps * |b dt| ~ 1e-13 of argument rounding).
+// n = rint(dt / P) whole periods are removed exactly (fma: rem = dt - n P with one rounding of a small number),
+// sincospi takes the remainder in units of pi, and sin(pi n + y) = (-1)^n sin y, cos likewise.
+__device__ __forceinline__ void phase_sincos(double dt, double P, double* s, double* c) {
+    const double n = rint(dt / P);
+    const double rem = fma(-n, P, dt);
+    double sv, cv;
+    sincospi(rem / P, &sv, &cv);
+    const bool odd = (((long long)n) & 1ll) != 0;
+    *s = odd ? -sv : sv;
+    *c = odd ? -cv : cv;
+}
+
 // shape value when sin(pi |r|/P) is already known (s); used by the tiled assembly fast path
 __device__ __forceinline__ double kern_shape_with_sin(const PKern& k, double r, double s) {
     switch (k.kind) {

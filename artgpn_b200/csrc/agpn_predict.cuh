@@ -19,7 +19,8 @@ struct PredArgs {
     const double* ttrain;    // [N]
     int M, N, n_pad, nblk;
     int series;
-    int square;              // M == N (WhiteNoise quirk inside K*)
+    int square;              // whole prediction grid has N points (WhiteNoise quirk inside K*)
+    int row_off = 0;         // index of this call's first prediction point inside the whole grid
     int exact;               // reference operation order for the K* entries
     const double* L;         // factor [n_pad][ld]
     int ld;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256, 2) predict_kernel(const __grid_constant__
                         if (gm < g.M && gn < g.N) {
                             const double t2 = s_tn[col];
                             const double r = t1 - t2;
-                            const bool dg = g.square && gm == gn;
+                            const bool dg = g.square && gm + g.row_off == gn;
                             for (int j = 0; j < q; ++j) {
                                 if (g.exact) {
                                     v = __dadd_rn(v, __dmul_rn(kern_value_exact(s_rweight[j], r, t1, t2, dg),

@@ -146,9 +146,8 @@ __global__ void __launch_bounds__(256) small_fused_kernel(const __grid_constant_
     if (g.fast) {
         for (int u = tid; u < q * np; u += 256) {
             const int j = u / np, n = u % np;
-            const double b = (s_node[j].kind == K_SE) ? 0.0 : s_node[j].b;
-            double sv, cv;
-            sincos(b * (tt[n] - g.torigin), &sv, &cv);
+            double sv = 0.0, cv = 1.0;
+            if (s_node[j].kind != K_SE) phase_sincos(tt[n] - g.torigin, s_node[j].per, &sv, &cv);
             trig[(2 * j) * np + n] = sv;
             trig[(2 * j + 1) * np + n] = cv;
         }

@@ -42,26 +42,59 @@ def gather_loglikes(local, W, group=None):
     return torch.cat([buf[r * mx:r * mx + sizes[r]] for r in range(world)])
 
 
+def init_comm(net, group=None):
+    """Bind an NCCL communicator over the ranks of `group` to the network's context (agpn_comm_init): rank 0 draws
+    the ncclUniqueId inside the library, torch.distributed only carries its 128 bytes to the other ranks.  Idempotent
+    per (network, group)."""
+    import torch.distributed as dist
+    from . import _lib
+    key = ("comm", id(group), dist.get_world_size(group), dist.get_rank(group))
+    if getattr(net, "_comm_key", None) == key and net._handle is not None:
+        return
+    lib = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [None]
+    if rank == 0:
+        buf = np.zeros(128, dtype=np.uint8)
+        _lib.check(lib.agpn_comm_unique_id(_lib.ptr(buf)))
+        box[0] = buf.tobytes()
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast_object_list(box, src=src, group=group)
+    idb = np.frombuffer(box[0], dtype=np.uint8).copy()
+    _lib.check(lib.agpn_comm_init(net._ctx(), _lib.ptr(idb), rank, world))
+    net._comm_key = key
+
+
 def log_likelihood_batch_sharded(net, theta, group=None, evaluator=None):
     """Log-likelihoods of all W rows of `theta` (same full array on every rank), computed
-    W / world_size rows per rank and gathered.  `evaluator(theta_slice) -> 1-D float64 torch tensor`
-    defaults to ``net.log_likelihood_batch`` on this rank's GPU."""
+    W / world_size rows per rank and gathered.
+
+    Default (GPU): one call into the C ABI (agpn_loglike_batch_sharded): the rank's rows are evaluated with the
+    results written into the gather buffer and one ncclAllGather on the current stream returns the [W] vector --
+    torch only hands over buffers.  `evaluator(theta_slice) -> 1-D float64 torch tensor` replaces the GPU evaluation
+    and gathers through torch.distributed instead (CPU / gloo tests of the partitioning logic)."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     W = theta.shape[0]
-    lo, hi = shard_bounds(W, world, rank)
-    mine = theta[lo:hi]
-    if evaluator is None:
-        if hi > lo:
-            if not torch.is_tensor(mine):
-                mine = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float64)).cuda(net._device)
-            local = net.log_likelihood_batch(mine)
-        else:
-            local = torch.empty(0, dtype=torch.float64, device="cuda:%d" % net._device)
-    else:
-        local = evaluator(mine)
-    return gather_loglikes(local, W, group)
+    if evaluator is not None:
+        lo, hi = shard_bounds(W, world, rank)
+        return gather_loglikes(evaluator(theta[lo:hi]), W, group)
+    from . import _lib
+    if net._structure is None:
+        raise RuntimeError("call set_structure(nodes, weights, means) first")
+    init_comm(net, group)
+    lib = _lib.load()
+    dev = torch.device("cuda", net._device)
+    if not torch.is_tensor(theta):
+        theta = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64)).to(dev)
+    if theta.dtype != torch.float64 or theta.dim() != 2 or theta.shape[1] != net._structure.D or theta.device != dev:
+        raise ValueError("theta must be float64 [W, %d] on cuda:%d" % (net._structure.D, net._device))
+    theta = theta.contiguous()
+    out = torch.empty(W, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.agpn_loglike_batch_sharded(net._ctx(), W, theta.data_ptr(), 1, out.data_ptr(), 1, None, stream))
+    return out
 
 
 def prediction_sharded(net, nodes, weights, means, jitters, time, dataset=1, group=None):

@@ -12,7 +12,14 @@ CONFIGS = {
     "C2": dict(N=167, p=3, q=1, W=256),
     "C3": dict(N=2048, p=3, q=2, W=128),
     "C4": dict(N=8192, p=3, q=3, W=32),
+    # BASELINE.json configs[4]: prediction on a 10^5-point grid per series from a 3 x 4096 fitted network
+    "C5": dict(N=4096, p=3, q=2, W=1, M=100000),
 }
+
+
+def prediction_grid(t, M):
+    """t* = linspace(t.min() - 5, t.max() + 5, M)."""
+    return np.linspace(t.min() - 5.0, t.max() + 5.0, M)
 
 
 def make_data(N, p=3, seed=0):
@@ -50,6 +57,41 @@ def make_walkers(W, p=3, q=2, weights="Constant", seed=1):
     for i in range(p):
         cols.append(JITTER_CENTRES[i % len(JITTER_CENTRES)] * rng.lognormal(0, 0.1, W))
     return np.ascontiguousarray(np.stack(cols, axis=1))
+
+
+# A second synthetic structure that the specialised assembly kernel does NOT cover (generic assemble_kernel):
+# nodes Matern52(ell) + RationalQuadratic(alpha, ell), Constant weights, Linear means.
+M52RQ_CENTRES = [(20.0,), (1.5, 40.0)]
+
+
+def make_walkers_m52rq(W, p=3, seed=1):
+    """theta[W][D] for nodes [Matern52(ell), RationalQuadratic(alpha, ell)], 2p Constant weights, p Linear means,
+    p jitters (same centres / spreads as make_walkers for the shared parts)."""
+    rng = np.random.default_rng(seed)
+    cols = []
+    for cs in M52RQ_CENTRES:
+        for c in cs:
+            cols.append(c * rng.lognormal(0, 0.1, W))
+    for i in range(p):
+        for j in range(2):
+            cols.append(WEIGHT_CENTRES[(j + 2 * i) % len(WEIGHT_CENTRES)] * rng.lognormal(0, 0.1, W))
+    for i in range(p):
+        cols.append(rng.normal(0, 0.02, W))
+        cols.append(rng.normal(0, 0.5, W))
+    for i in range(p):
+        cols.append(JITTER_CENTRES[i % len(JITTER_CENTRES)] * rng.lognormal(0, 0.1, W))
+    return np.ascontiguousarray(np.stack(cols, axis=1))
+
+
+def objects_from_row_m52rq(mod_node, mod_weight, mod_mean, row, p=3):
+    row = list(map(float, row))
+    nodes = [mod_node.Matern52(row[0]), mod_node.RationalQuadratic(row[1], row[2])]
+    k = 3
+    ws = [mod_weight.Constant(row[k + i]) for i in range(2 * p)]
+    k += 2 * p
+    means = [mod_mean.Linear(row[k + 2 * i], row[k + 2 * i + 1]) for i in range(p)]
+    k += 2 * p
+    return nodes, ws, means, row[k:k + p]
 
 
 def structure_names(p=3, q=2, weights="Constant"):

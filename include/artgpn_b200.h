@@ -98,6 +98,25 @@ int agpn_loglike_batch(agpn_ctx* ctx, int W, const double* theta, int theta_on_d
                        double* out, int out_on_device, int* status, void* stream);
 
 /*
+ * Walker sharding over the GPUs of one box (one process per GPU).  The reference's only parallelism is a process
+ * pool over emcee walkers (examples/Sun/01_emcee.py:119-122); here the W rows of a batch are block-partitioned over
+ * the ranks of an NCCL communicator (rows [lo, hi) of rank r: contiguous blocks, the first W % nranks ranks get one
+ * more), every rank evaluates its rows on its own GPU with the result written straight into its slot of the gather
+ * buffer, and ONE ncclAllGather on `stream` returns all W log-likelihoods on every rank.  No matrix is split across
+ * GPUs: every value is bit-identical to a single-GPU agpn_loglike_batch.
+ *   agpn_comm_unique_id: fills 128 bytes (an ncclUniqueId) -- call on one rank, distribute by any means.
+ *   agpn_comm_init: collective over all ranks; binds the communicator to ctx (released by agpn_destroy).
+ *   agpn_loglike_batch_sharded: collective; theta[W][D] is the FULL batch (same on every rank), out[W] / status[W]
+ *   receive the full result on every rank.  NCCL is resolved at run time (dlopen of libnccl.so.2; an already loaded
+ *   copy, e.g. torch's, is reused); the library has no link-time NCCL dependency.
+ */
+int agpn_comm_unique_id(void* id128_out);
+int agpn_comm_init(agpn_ctx* ctx, const void* nccl_unique_id128, int rank, int nranks);
+int agpn_comm_rank(const agpn_ctx* ctx, int* rank, int* nranks);
+int agpn_loglike_batch_sharded(agpn_ctx* ctx, int W, const double* theta, int theta_on_device,
+                               double* out, int out_on_device, int* status, void* stream);
+
+/*
  * Replaces network._covariance_matrix (arttwo.py:151-192) and the K* loop of prediction
  * (arttwo.py:373-384): out[na][nb] = sum_j W_{series,j}(ta,tb) * F_j(ta,tb) for one theta row.
  *   ta == NULL / tb == NULL mean the training grid.  `square_quirk` != 0 makes WhiteNoise put
@@ -117,6 +136,16 @@ int agpn_covariance_block(agpn_ctx* ctx, const double* theta, int series,
 int agpn_mean_table(agpn_ctx* ctx, const double* theta, const double* t, int n, double* out);
 
 /*
+ * The same mean functions (mean.py:68-202, network._mean arttwo.py:106-126) without a context: the
+ * classes and parameters travel with the call -- mean_nterms[p] terms per series (0 == None; a mean.Sum
+ * is several terms), mean_kind[sum] and pars[] = the terms' .pars back to back -- so no context's
+ * structure is touched.  Linear is centred on mean(t), Keplerian anchored at t[0] (mean.py:92,175).
+ * out[p][n]; host pointers; runs on `device`.
+ */
+int agpn_mean_eval(int device, int p, const int* mean_nterms, const int* mean_kind, const double* pars,
+                   const double* t, int n, double* out);
+
+/*
  * Replaces network.prediction (arttwo.py:329-396) for one theta row and one series (0-based):
  * mean_out[M] = K* K^-1 r + m(t*), std_out[M] = sqrt(diag(K** + s^2 I - K* K^-1 K*^T)).
  * All pointers host.  *status receives AGPN_STATUS_* of the factorisation (the reference lets
@@ -127,14 +156,16 @@ int agpn_predict(agpn_ctx* ctx, const double* theta, int series, int M, const do
 
 /*
  * agpn_predict for a SLICE of a larger prediction grid (multi-GPU: the grid is split over ranks, SURVEY
- * section 8(e)).  mean.Linear is centred on the mean of the WHOLE grid and mean.Keplerian anchored at its
- * first point (mean.py:92,175), so both are passed in.  Not valid for a Keplerian mean whose "any |M1| >
- * 1e-10" test (mean.py:180) would differ between the slice and the whole grid, nor for WhiteNoise kernels
- * when the whole grid has exactly N points (the square-lag quirk is evaluated per slice).
+ * section 8(e)): tstar[M] = whole_grid[grid_offset : grid_offset + M] of a grid of grid_M points.
+ * mean.Linear is centred on the mean of the WHOLE grid and mean.Keplerian anchored at its first point
+ * (mean.py:92,175), so both are passed in; WhiteNoise's square-lag quirk inside K* (node.py:68-72) is
+ * decided by the whole grid too: wn^2 iff grid_M == N and (grid_offset + row) == training index, whatever
+ * the slice length -- results do not depend on how the grid is split.  Not valid for a Keplerian mean whose
+ * "any |M1| > 1e-10" test (mean.py:180) would differ between the slice and the whole grid.
  */
 int agpn_predict_slice(agpn_ctx* ctx, const double* theta, int series, int M, const double* tstar,
-                       double grid_mean, double grid_t0, double* mean_out, double* std_out, int* status,
-                       void* stream);
+                       int grid_M, int grid_offset, double grid_mean, double grid_t0,
+                       double* mean_out, double* std_out, int* status, void* stream);
 
 /*
  * Predictive mean AND full covariance (what y_cov of arttwo.py:393 / the legacy art.py:350-354 hold):
@@ -166,6 +197,15 @@ int agpn_kernel_eval(int device, int family, int kind, const double* pars,
  */
 int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, double* rhs,
                        double* logdet, double* quad, int* info, void* stream);
+
+/*
+ * Replaces network.sample (arttwo.py:129-147: scipy multivariate_normal(0, K, allow_singular=True).rvs()):
+ * out[nsamp][n] = L z_s with K (+ nugget I) = L L^T factorised by the batched Cholesky kernels and z[nsamp][n]
+ * standard-normal draws supplied by the caller (the random stream stays on the host side, like the reference's).
+ * allow_singular: a positive SEMI-definite K is shifted by the smallest nugget of 1e-14 max|K_ii| x 100^k (k <= 4) that makes
+ * it factorisable; an indefinite K is an error (*nugget_used, may be NULL; 0 for a definite K).  Host pointers; runs on `device`.
+ */
+int agpn_mvn_sample(int device, int n, const double* K, int nsamp, const double* z, double* out, double* nugget_used);
 
 /* Measured issue-rate peak of the FP64 tensor instruction (DMMA.8x8x4) on `device`, in TFLOP/s:
  * the denominator bench.py uses for the Cholesky roofline (MEASURED_PEAKS.json has no FP64 figure). */
