@@ -59,6 +59,8 @@ _SIGNATURES = {
     "agpn_phase_ms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "agpn_update_path": (ctypes.c_int, [c_void_p]),
     "agpn_predict_path": (ctypes.c_int, [c_void_p]),
+    "agpn_timeline_dump": (ctypes.c_int, [c_void_p, ctypes.c_char_p]),
+    "agpn_mega_prof": (ctypes.c_int, [c_void_p, c_void_p]),
     "agpn_slice_ms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
 }
 

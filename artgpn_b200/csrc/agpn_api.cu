@@ -21,6 +21,7 @@
 #include "agpn_small.cuh"
 #include "agpn_tma.cuh"
 #include "agpn_i8.cuh"
+#include "agpn_mega.cuh"
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
@@ -87,7 +88,8 @@ struct agpn_ctx {
     double* d_rhs = nullptr;
     double* d_logdet = nullptr;
     double* d_quad = nullptr;
-    int* d_info = nullptr;     // info | kflag | rflag, 3 * cap_mats
+    int* d_info = nullptr;     // info | kflag | rflag | refine, 4 * cap_mats
+    double refine_ratio = 1.0e3;   // AGPN_REFINE_RATIO: pivot ratio of a diagonal block above which its panel is solved by substitution
     size_t cap_w = 0;
     double* d_theta = nullptr;
     double* d_out = nullptr;
@@ -116,7 +118,9 @@ struct agpn_ctx {
     bool profiling = false;
     double phase_ms[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
     long long phase_launches[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
-    struct Ev { cudaEvent_t a, b; int ph; };
+    struct Ev { cudaEvent_t a, b; int ph; int stream_id; };
+    bool timeline = false;     // AGPN_TIMELINE=1: events around every launch WITHOUT serialising the sub-batch streams (agpn_timeline_dump)
+    size_t timeline_used = 0;
     std::vector<Ev> evs;
     bool attrs_set = false;
     // TMA descriptors of the batch workspace d_A (box 128 x 16 and 64 x 16 doubles, 128-byte swizzle)
@@ -132,6 +136,7 @@ struct agpn_ctx {
     int i8_clusters = 74;          // persistent clusters per launch = SMs / 2
     int i8_clusters_max = 74;
     bool i8_clusters_fixed = false;   // AGPN_I8_CLUSTERS given
+    bool i8_balance = false;          // AGPN_I8_BALANCE=1: equal tile counts per persistent cluster (measured: no gain at 16 walkers, -1.7 % at 128)
     bool fuse_slices = true;       // AGPN_I8_FUSE=0: separate i8_slice_kernel after every panel solve
     int i8_group = 8;              // group of the INT8 path: all block columns (pure left-looking) unless AGPN_GROUP is given
     signed char* d_S8 = nullptr;   // [cap_mats] digit planes of one group of block columns
@@ -162,6 +167,12 @@ struct agpn_ctx {
     bool lookahead_forced = false;     // AGPN_LOOKAHEAD=2: for every batch size (default: few matrices only)
     cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_la[8][2] = {};
+    // persistent tile-task kernel (agpn_mega.cuh): one launch per wave instead of the per-column chain (AGPN_MEGA=0 disables)
+    bool use_mega = true;
+    int* d_mega = nullptr;         // fD | fP | fU | refine per block, ints
+    size_t cap_mega = 0;
+    int linv_blocks = 1;           // inverse blocks kept per matrix in d_Linv (nblk with the task kernel)
+    unsigned long long* d_megaprof = nullptr;   // AGPN_MEGA_PROF=1: [CTAs][16] time / count slots of the task kernel (agpn_mega_prof)
     // walker sharding over the GPUs of one box (agpn_comm_init / agpn_loglike_batch_sharded)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -238,6 +249,7 @@ static int set_kernel_attrs(agpn_ctx* c) {
     CUDA_TRY(cudaFuncSetAttribute(syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(syrk_i8_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(chol_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
     // function attributes are per function (not per context): always allow the largest K0 configuration
     {
         cudaFuncAttributes fa;
@@ -275,8 +287,14 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     c->i8_which = i8_mode_from_env();
     if (const char* e = getenv("AGPN_I8_FUSE")) c->fuse_slices = atoi(e) != 0;
     if (const char* e = getenv("AGPN_I8_PERSIST")) c->i8_persist = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_I8_BALANCE")) c->i8_balance = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_MEGA")) c->use_mega = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_MEGA_PROF")) if (atoi(e) != 0) {
+        if (cudaMalloc(&c->d_megaprof, sizeof(unsigned long long) * 16 * 2 * c->i8_clusters_max) != cudaSuccess) { cudaGetLastError(); c->d_megaprof = nullptr; }
+    }
     if (const char* e = getenv("AGPN_PREDICT")) c->predict_dmma = strcmp(e, "dmma") == 0;
     if (const char* e = getenv("AGPN_I8_TEST_WRAP")) c->predict_test_wrap = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_REFINE_RATIO")) c->refine_ratio = atof(e);
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -304,6 +322,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
         return 1;
     }
     if (const char* e = getenv("AGPN_GRAPH")) c->use_graph = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_TIMELINE")) c->timeline = atoi(e) != 0;
     if (cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_gin, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_gout, cudaEventDisableTiming) != cudaSuccess)
@@ -355,7 +374,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_S8); cudaFree(c->d_rscale);
     cudaFree(c->d_paug); cudaFree(c->d_ps8); cudaFree(c->d_pvec);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
-    cudaFree(c->d_gather); cudaFree(c->d_gstatus);
+    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof);
     agpn_comm_release(c);
     delete c;
     return 0;
@@ -440,6 +459,43 @@ extern "C" int agpn_slice_ms(agpn_ctx* c, double* ms, long long* launches) {
     return 0;
 }
 
+// AGPN_TIMELINE=1 diagnostics: start / end (ms after the first launch of the call) of every launch of the last
+// agpn_loglike_batch, with its phase and sub-batch stream -- the concurrency picture of the sub-batch streams
+extern "C" int agpn_timeline_dump(agpn_ctx* c, const char* path) {
+    if (!c || !path) USAGE_FAIL("agpn_timeline_dump: null pointer");
+    if (!c->timeline || c->timeline_used == 0) USAGE_FAIL("agpn_timeline_dump: no timeline (create the context with AGPN_TIMELINE=1)");
+    FILE* f = fopen(path, "w");
+    if (!f) USAGE_FAIL("agpn_timeline_dump: cannot open the output file");
+    fprintf(f, "launch,phase,stream,start_ms,end_ms\n");
+    for (size_t i = 0; i < c->timeline_used; ++i) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, c->evs[0].a, c->evs[i].a);
+        cudaEventElapsedTime(&b, c->evs[0].a, c->evs[i].b);
+        fprintf(f, "%zu,%d,%d,%.4f,%.4f\n", i, c->evs[i].ph, c->evs[i].stream_id, a, b);
+    }
+    fclose(f);
+    return 0;
+}
+
+// AGPN_MEGA_PROF=1 diagnostics: per-CTA means of the task kernel's time slots (microseconds / counts) of the last wave:
+// 0 U runs, 1 U tasks, 2 D body, 3 D wait, 4 D tasks, 5 P body, 6 P wait, 7 P tasks (group 0), 8 whole kernel,
+// 9 cluster sync before U runs, 10 producer waits for panels
+extern "C" int agpn_mega_prof(agpn_ctx* c, double* out16) {
+    if (!c || !out16) USAGE_FAIL("agpn_mega_prof: null pointer");
+    if (!c->d_megaprof) USAGE_FAIL("agpn_mega_prof: create the context with AGPN_MEGA_PROF=1");
+    ENTER_DEVICE(c->device);
+    const int nct = 2 * c->i8_clusters_max;
+    std::vector<unsigned long long> h((size_t)16 * nct);
+    CUDA_TRY(cudaMemcpy(h.data(), c->d_megaprof, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+    for (int s = 0; s < 16; ++s) {
+        double acc = 0.0;
+        for (int b = 0; b < nct; ++b) acc += (double)h[(size_t)b * 16 + s];
+        const bool is_count = (s == 1 || s == 4 || s == 7);
+        out16[s] = acc / nct / (is_count ? 1.0 : 1000.0);
+    }
+    return 0;
+}
+
 extern "C" int agpn_update_path(const agpn_ctx* c) { return c ? c->i8_which : -1; }
 extern "C" int agpn_predict_path(const agpn_ctx* c) { return c ? c->last_predict_path : -1; }
 
@@ -449,7 +505,7 @@ struct PhaseScope {
     cudaStream_t st;
     size_t idx;
     bool on;
-    PhaseScope(agpn_ctx* c_, cudaStream_t st_, int ph, size_t& cursor) : c(c_), st(st_), idx(0), on(c_->profiling) {
+    PhaseScope(agpn_ctx* c_, cudaStream_t st_, int ph, size_t& cursor) : c(c_), st(st_), idx(0), on(c_->profiling || c_->timeline) {
         c->phase_launches[ph] += 1;
         if (!on) return;
         if (cursor >= c->evs.size()) {
@@ -461,6 +517,11 @@ struct PhaseScope {
         }
         idx = cursor++;
         c->evs[idx].ph = ph;
+        c->evs[idx].stream_id = -1;
+        for (int i = 0; i < 8; ++i) {
+            if (st == c->sub[i] && st) c->evs[idx].stream_id = i;
+            if (st == c->side[i] && st) c->evs[idx].stream_id = 8 + i;
+        }
         cudaEventRecord(c->evs[idx].a, st);
     }
     ~PhaseScope() {
@@ -469,6 +530,7 @@ struct PhaseScope {
 };
 
 static void collect_phases(agpn_ctx* c, size_t used) {
+    if (c->timeline) c->timeline_used = used;
     if (!c->profiling) return;
     for (size_t i = 0; i < used; ++i) {
         float ms = 0.f;
@@ -476,6 +538,33 @@ static void collect_phases(agpn_ctx* c, size_t used) {
         cudaEventElapsedTime(&ms, c->evs[i].a, c->evs[i].b);
         c->phase_ms[c->evs[i].ph] += ms;
     }
+}
+
+// The persistent tile-task kernel covers the default configuration of the INT8-sliced path: purely left-looking (one group
+// of all block columns), digit planes written by the panel solve, from three block columns on.
+static bool mega_eligible(const agpn_ctx* c) {
+    return c->use_mega && c->i8_which == 3 && c->i8_persist && c->fuse_slices && c->nblk > 2 && c->i8_group >= c->nblk &&
+           !c->use_tma;
+}
+
+// one launch for the whole factorisation: flags = fD[nmat] | fP[nmat][nrows] | fU[nmat][nrows] (zeroed here);
+// ncols block columns are eliminated (ncols < g.nblk: block rows appended below a square block, prediction)
+static int launch_mega(agpn_ctx* c, CholArgs& g, int* flags, int ncols, cudaStream_t st) {
+    const size_t nm = (size_t)g.nmat, nr = (size_t)g.nblk;
+    CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * nm * (1 + 2 * nr), st));
+    MegaArgs m;
+    m.fD = flags; m.fP = flags + nm; m.fU = flags + nm + nm * nr;
+    m.ncols = ncols;
+    m.tflags = 1 | (g.keep_factor ? 0 : 2);
+    m.prof = c->d_megaprof;
+    if (m.prof) CUDA_TRY(cudaMemsetAsync(m.prof, 0, sizeof(unsigned long long) * 16 * 2 * c->i8_clusters_max, st));
+    int ncl = c->i8_clusters_max;
+    const long long work = (long long)g.nmat * g.nblk;           // no point in more clusters than the widest segment has tasks
+    if (work < ncl) ncl = (int)work;
+    if (ncl < 1) ncl = 1;
+    chol_mega_kernel<<<2 * ncl, MEGA_THREADS, MEGA_SMEM_BYTES, st>>>(g, m);
+    LAUNCH_CHECK();
+    return 0;
 }
 
 // ---- workspace -------------------------------------------------------------------------------
@@ -491,11 +580,20 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_A, sizeof(double) * nmat * np * np));
         c->maps_valid = c->use_tma && make_batch_map(&c->tmA, c->d_A, nmat, c->npad, c->npad, TB) &&
                         make_batch_map(&c->tmB, c->d_A, nmat, c->npad, c->npad, BN);
-        CUDA_TRY(cudaMalloc(&c->d_Linv, sizeof(double) * nmat * TB * TB));
+        c->linv_blocks = mega_eligible(c) ? c->nblk : 1;
+        CUDA_TRY(cudaMalloc(&c->d_Linv, sizeof(double) * nmat * c->linv_blocks * TB * TB));
         CUDA_TRY(cudaMalloc(&c->d_rhs, sizeof(double) * nmat * np));
         CUDA_TRY(cudaMalloc(&c->d_logdet, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
-        CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 3 * nmat));
+        CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 4 * nmat));
+        if (mega_eligible(c)) {
+            cudaFree(c->d_mega);
+            c->d_mega = nullptr;
+            c->cap_mega = 0;
+            const size_t ni = nmat * (1 + 3 * (size_t)c->nblk);
+            CUDA_TRY(cudaMalloc(&c->d_mega, sizeof(int) * ni));
+            c->cap_mega = ni;
+        }
         if (c->i8_which && c->nblk > 2) {
             c->sgroup = c->i8_group < 2 ? 2 : c->i8_group;
             CUDA_TRY(cudaMalloc(&c->d_S8, nmat * i8_slices_per_matrix(c->nblk, c->sgroup)));
@@ -528,6 +626,16 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
 // look-ahead (side stream + two events, INT8 left-looking updates only): column k's diagonal tile is updated first and
 // factorised on `st` while the update of the tiles below it runs on `side`; the panel solve joins both.
 struct LookAhead { cudaStream_t side; cudaEvent_t fork, join; };
+// persistent clusters of one update launch: every cluster walks the same number of tiles (+-1), so no cluster idles through
+// a last partial wave -- the SMs a launch does not need stay free for the other sub-batch streams
+// (AGPN_I8_BALANCE=1; default off = min(tiles, limit) clusters: measured 3.233 vs 3.245 ms at 16 walkers, 21.49 vs 21.12 ms at 128)
+static int balanced_clusters(const agpn_ctx* c, int total) {
+    const int lim = c->i8_clusters < 1 ? 1 : c->i8_clusters;
+    if (total <= lim) return total;
+    if (!c->i8_balance) return lim;
+    const int waves = (total + lim - 1) / lim;
+    return (total + waves - 1) / waves;
+}
 static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* cursor, int kstop = -1, bool no_trailing = false,
                         const LookAhead* la = nullptr) {
     size_t local_cursor = 0;
@@ -548,16 +656,16 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
                 if ((i8 & 1) && c->i8_persist && la != nullptr && g.nblk - k > 1) {
                     CUDA_TRY(cudaEventRecord(la->fork, st));
                     CUDA_TRY(cudaStreamWaitEvent(la->side, la->fork, 0));
-                    const int ncl_d = g.nmat < c->i8_clusters ? g.nmat : c->i8_clusters;
+                    const int ncl_d = balanced_clusters(c, g.nmat);
                     syrk_i8_persistent_kernel<<<2 * ncl_d, I8_THREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, 1, g.nmat, 0);
                     LAUNCH_CHECK();
                     const int ntl = g.nblk - k - 1, total = ntl * g.nmat;
-                    const int ncl = total < c->i8_clusters ? total : c->i8_clusters;
+                    const int ncl = balanced_clusters(c, total);
                     syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, la->side>>>(g, k - k0, k, 1, ntl, total, 1);
                     CUDA_TRY(cudaEventRecord(la->join, la->side));
                 } else if ((i8 & 1) && c->i8_persist) {
                     const int ntl = g.nblk - k, total = ntl * g.nmat;
-                    const int ncl = total < c->i8_clusters ? total : c->i8_clusters;
+                    const int ncl = balanced_clusters(c, total);
                     syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, ntl, total, 0);
                 } else if (i8 & 1)
                     syrk_i8_kernel<<<dim3(2 * (g.nblk - k), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
@@ -597,7 +705,7 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
             PhaseScope ps(c, st, PH_SYRK, cur);
             if ((i8 & 2) && c->i8_persist) {
                 const int ntl = nt * (nt + 1) / 2, total = ntl * g.nmat;
-                const int ncl = total < c->i8_clusters ? total : c->i8_clusters;
+                const int ncl = balanced_clusters(c, total);
                 syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, kend - k0, kend, 0, ntl, total, 0);
             } else if (i8 & 2)
                 syrk_i8_kernel<<<dim3(nt * (nt + 1), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
@@ -669,7 +777,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     const double half_n_log2pi = 0.5 * (double)c->N * std::log(2.0 * AGPN_PI);
     CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double) * nmat, st));
     CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double) * nmat, st));
-    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 3 * c->cap_mats, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 4 * c->cap_mats, st));
     int* d_infoflag = c->d_info;
     int* d_kflag = c->d_info + c->cap_mats;
     int* d_rflag = c->d_info + 2 * c->cap_mats;
@@ -714,8 +822,9 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     }
     CholArgs g;
     g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = nmat;
-    g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
+    g.Linv = c->d_Linv; g.linv_blocks = c->linv_blocks; g.rhs = c->d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad;
     g.info = d_infoflag;
+    g.refine = c->d_info + 3 * c->cap_mats; g.refine_ratio = c->refine_ratio;
     g.A0 = c->d_A; g.mat0 = 0;
     c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
     // two block columns: a single depth-128 update, where the per-tile cost of the INT8 kernel still outweighs its
@@ -739,7 +848,12 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         LAUNCH_CHECK();
     }
     const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
-    if (nsub == 1) {
+    if (mega_eligible(c) && g.S8 && c->d_mega && !c->profiling && !c->timeline) {
+        // the whole factorisation as ONE persistent launch of tile tasks (agpn_mega.cuh)
+        g.refine = c->d_mega + (size_t)nmat * (1 + 2 * (size_t)c->nblk); g.refine_blocks = c->nblk;
+        PhaseScope ps(c, st, PH_SYRK, cur);
+        if (launch_mega(c, g, c->d_mega, c->nblk, st)) return 1;
+    } else if (nsub == 1) {
         if (run_cholesky(c, g, st, &cur)) return 1;
     } else {
         // fork: every sub-stream waits for the assembly, factorises its slice of the matrices
@@ -749,11 +863,12 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             const int m0 = (int)((long long)nmat * si / nsub), m1 = (int)((long long)nmat * (si + 1) / nsub);
             CholArgs gs = g;
             gs.A = g.A + (size_t)m0 * g.mat_stride;
-            gs.Linv = g.Linv + (size_t)m0 * TB * TB;
+            gs.Linv = g.Linv + (size_t)m0 * g.linv_blocks * TB * TB;
             gs.rhs = g.rhs + (size_t)m0 * np;
             gs.logdet = g.logdet + m0;
             gs.quad = g.quad + m0;
             gs.info = g.info + m0;
+            gs.refine = g.refine + (size_t)m0 * g.refine_blocks;
             gs.nmat = m1 - m0;
             gs.mat0 = m0;
             if (g.S8) {
@@ -764,7 +879,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             const LookAhead la = {c->side[si], c->ev_la[si][0], c->ev_la[si][1]};
             // measured (3 x 2048): +4 % at 8 walkers, nothing at 16, -2 % at 128; 3 x 8192, 4 walkers: +2 %
             const bool use_la = c->lookahead && gs.S8 && (c->lookahead_forced || nmat <= 24);
-            if (run_cholesky(c, gs, c->sub[si], nullptr, -1, false, use_la ? &la : nullptr)) return 1;
+            if (run_cholesky(c, gs, c->sub[si], c->timeline ? &cur : nullptr, -1, false, use_la ? &la : nullptr)) return 1;
             CUDA_TRY(cudaEventRecord(c->ev_join[si], c->sub[si]));
             CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[si], 0));
         }
@@ -882,7 +997,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
         size_t cur = 0;
         double* d_out = out_on_device ? out + w0 : c->d_out;
         bool replayed = false;
-        if (c->use_graph && !c->profiling) {
+        if (c->use_graph && !c->profiling && !c->timeline) {
             const int grc = run_wave_graph(c, Ww, theta + w0 * D, theta_on_device, d_out, st, &replayed);
             if (grc) return grc;
         }
@@ -898,7 +1013,7 @@ extern "C" int agpn_loglike_batch(agpn_ctx* c, int W, const double* theta, int t
             CUDA_TRY(cudaMemcpyAsync(out + w0, c->d_out, sizeof(double) * Ww, cudaMemcpyDeviceToHost, st));
         if (status) CUDA_TRY(cudaMemcpyAsync(status + w0, c->d_status, sizeof(int) * Ww, cudaMemcpyDeviceToHost, st));
         const bool more = w0 + wave < (size_t)W;
-        if (!out_on_device || status || c->profiling || more) CUDA_TRY(cudaStreamSynchronize(st));
+        if (!out_on_device || status || c->profiling || c->timeline || more) CUDA_TRY(cudaStreamSynchronize(st));
         collect_phases(c, cur);
     }
     return 0;
@@ -1013,7 +1128,7 @@ extern "C" int agpn_loglike_batch_sharded(agpn_ctx* c, int W, const double* thet
     const int slot = (W + c->nranks - 1) / c->nranks;
     const size_t need = (size_t)slot * c->nranks + (size_t)W;
     if (need > c->cap_gather) {
-        cudaFree(c->d_gather); cudaFree(c->d_gstatus);
+        cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof);
         c->d_gather = nullptr; c->d_gstatus = nullptr; c->cap_gather = 0;
         CUDA_TRY(cudaMalloc(&c->d_gather, sizeof(double) * need));
         CUDA_TRY(cudaMalloc(&c->d_gstatus, sizeof(int) * need));
@@ -1253,6 +1368,7 @@ static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, int grid
     g.A = c->d_paug; g.mat_stride = (long long)(T * np); g.ld = c->npad; g.nblk = nrt; g.nmat = 1;
     g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad; g.info = c->d_info;
     g.A0 = c->d_paug; g.mat0 = 0;
+    g.refine = c->d_info + 3 * c->cap_mats; g.refine_ratio = c->refine_ratio;
     g.keep_factor = 1;                          // V is read back for the row sums of squares
     if (c->nblk > 1) {
         g.S8 = c->d_ps8; g.rscale = d_rs; g.sgroup = sgroup; g.i8flag = d_flag;
@@ -1302,7 +1418,7 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
     CUDA_TRY(cudaMemcpyAsync(d_ts, tstar, sizeof(double) * M, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 3 * c->cap_mats, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 4 * c->cap_mats, st));
     int* d_kflag = c->d_info + c->cap_mats;
     int* d_rflag = c->d_info + 2 * c->cap_mats;
     // residual of the chosen series (arttwo.py:359-365)
@@ -1440,7 +1556,7 @@ extern "C" int agpn_predict_cov(agpn_ctx* c, const double* theta, int series, in
     CUDA_TRY(cudaMemsetAsync(d_rhs, 0, sizeof(double) * T, st));
     CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 3 * c->cap_mats, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 4 * c->cap_mats, st));
     int* d_kflag = c->d_info + c->cap_mats;
     int* d_rflag = c->d_info + 2 * c->cap_mats;
     MeanArgs m;
@@ -1472,6 +1588,7 @@ extern "C" int agpn_predict_cov(agpn_ctx* c, const double* theta, int series, in
     g.A = c->d_aug; g.mat_stride = (long long)(T * T); g.ld = (int)T; g.nblk = (int)(T / TB); g.nmat = 1;
     g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad; g.info = c->d_info;
     g.A0 = c->d_aug; g.mat0 = 0;
+    g.refine = c->d_info + 3 * c->cap_mats; g.refine_ratio = c->refine_ratio;
     const bool maps_were = c->maps_valid;
     c->maps_valid = false;                      // the tensor maps describe the batch workspace, not this matrix
     c->group_eff = c->group_fixed ? c->group : 2;
@@ -1542,6 +1659,9 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     if (set_kernel_attrs(&tmp)) return 1;
     DevBuf b_linv, b_rs;
     struct ByteBuf { signed char* p = nullptr; ~ByteBuf() { if (p) cudaFree(p); } } b_s8;
+    struct IntBuf { int* p = nullptr; ~IntBuf() { if (p) cudaFree(p); } } b_refine;
+    CUDA_TRY(cudaMalloc(&b_refine.p, sizeof(int) * nmat));
+    CUDA_TRY(cudaMemsetAsync(b_refine.p, 0, sizeof(int) * nmat, st));
     CUDA_TRY(b_linv.alloc((size_t)nmat * TB * TB));
     double* d_linv = b_linv.p;
     CUDA_TRY(cudaMemsetAsync(logdet, 0, sizeof(double) * nmat, st));
@@ -1550,6 +1670,8 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     CholArgs g;
     g.A = A; g.mat_stride = (long long)n_pad * n_pad; g.ld = n_pad; g.nblk = n_pad / TB; g.nmat = nmat; g.Linv = d_linv;
     g.linv_blocks = 1; g.rhs = rhs; g.logdet = logdet; g.quad = quad; g.info = info;
+    g.refine = b_refine.p;
+    if (const char* e = getenv("AGPN_REFINE_RATIO")) g.refine_ratio = atof(e);
     g.A0 = A; g.mat0 = 0;
     if (const char* e = getenv("AGPN_SYRK")) { tmp.use_tma = strncmp(e, "tma", 3) == 0; tmp.tma_mc = strcmp(e, "tma_nomc") != 0; }
     tmp.maps_valid = tmp.use_tma && make_batch_map(&tmp.tmA, A, nmat, n_pad, n_pad, TB) && make_batch_map(&tmp.tmB, A, nmat, n_pad, n_pad, BN);

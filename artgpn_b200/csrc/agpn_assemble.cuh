@@ -222,28 +222,32 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ S
 // ---------------------------------------------------------------------------------------------
 #define ASMF_MAXQ 4
 
-// e^x for x <= 0 (NaN propagates, x < -708 flushes to 0): 2^k * P11(r), |r| <= ln2/2
-__device__ __forceinline__ double exp_nonpos(double x) {
-    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
-    const int k = __double2loint(t);
+// e^x for x <= 0 (NaN propagates, x < -708 flushes to 0): x = (16 k + j) ln2 / 16 + r, |r| <= ln2 / 32,
+// e^x = 2^k * 2^(j/16) * P6(r).  The sixteen 2^(j/16) sit in shared memory (`tab`: 128 bytes = each entry on its own pair
+// of banks, equal indices broadcast -> conflict free); P6 is the degree-6 Chebyshev fit of e^r on the interval (exact
+// rational arithmetic, max error 7e-18) -- 11 FP64 operations instead of the 17 of a table-free degree-11 polynomial.
+__constant__ double c_exp2_16[16] = {
+    0x1.0000000000000p+0, 0x1.0b5586cf9890fp+0, 0x1.172b83c7d517bp+0, 0x1.2387a6e756238p+0,
+    0x1.306fe0a31b715p+0, 0x1.3dea64c123422p+0, 0x1.4bfdad5362a27p+0, 0x1.5ab07dd485429p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.7a11473eb0187p+0, 0x1.8ace5422aa0dbp+0, 0x1.9c49182a3f090p+0,
+    0x1.ae89f995ad3adp+0, 0x1.c199bdd85529cp+0, 0x1.d5818dcfba487p+0, 0x1.ea4afa2a490dap+0};
+
+__device__ __forceinline__ double exp_nonpos(double x, const double* __restrict__ tab) {
+    const double t = fma(x, 23.083120654223414, 6755399441055744.0);          // 16 / ln2; low word of t = n = 16 k + j
+    const int n = __double2loint(t);
     const double kd = t - 6755399441055744.0;
-    double r = fma(kd, -6.93147180369123816490e-01, x);
-    r = fma(kd, -1.90821492927058770002e-10, r);
-    // degree-11 Chebyshev-economised Taylor polynomial on |r| <= 0.34658 (exact rational arithmetic,
-    // max relative error 1.6e-17; the plain Taylor series would need degree 13)
-    double p = 2.51148724919075077e-08;
-    p = fma(p, r, 2.76326434649757460e-07);
-    p = fma(p, r, 2.75572249492480561e-06);
-    p = fma(p, r, 2.48014854716773866e-05);
-    p = fma(p, r, 1.98412699092272865e-04);
-    p = fma(p, r, 1.38888889523250880e-03);
-    p = fma(p, r, 8.33333333330952240e-03);
-    p = fma(p, r, 4.16666666664880572e-02);
-    p = fma(p, r, 1.66666666666667018e-01);
-    p = fma(p, r, 5.00000000000001887e-01);
+    double r = fma(kd, -0.04332169877307024, x);                               // ln2 / 16, high 32 bits (kd * hi is exact)
+    r = fma(kd, -1.1926343307941173e-11, r);
+    double p = 0x1.6c181f479b148p-10;
+    p = fma(p, r, 0x1.11126eecbabeap-7);
+    p = fma(p, r, 0x1.55555554ad3e3p-5);
+    p = fma(p, r, 0x1.555555540526ep-3);
+    p = fma(p, r, 0x1.0000000000003p-1);
+    p = fma(p, r, 0x1.000000000000ap+0);
     p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const double scale = __hiloint2double((k + 1023) << 20, 0);
+    const double tv = tab[n & 15];
+    // tv * 2^k by adding k to the exponent field: x >= -708 keeps the result normal
+    const double scale = __hiloint2double(__double2hiint(tv) + ((n >> 4) << 20), __double2loint(tv));
     return (x < -708.0) ? 0.0 : p * scale;
 }
 
@@ -252,7 +256,7 @@ __device__ __forceinline__ void asm_fast_rows(const AsmArgs& g, int q, int w, in
                                               const double (*s_a)[2], const double (*s_amp)[ASMF_MAXQ],
                                               const double (*s_cs)[ASMF_MAXQ], const double (*s_rowt)[2][ASM_TILE],
                                               const double (*s_colt)[2][ASM_TILE], const double* s_ta, const double* s_tb,
-                                              const double (*s_diag)[ASM_TILE], double (&chk)[P]) {
+                                              const double (*s_diag)[ASM_TILE], const double* s_etab, double (&chk)[P]) {
     const int tid = threadIdx.x;
     const int tx = tid & 63, ty = tid >> 6;
     const int c0 = 2 * tx;
@@ -276,7 +280,7 @@ __device__ __forceinline__ void asm_fast_rows(const AsmArgs& g, int q, int w, in
             const double q0 = a * s0 * s0, q1 = a * s1 * s1;
             if (!WSE) {
                 const double c = s_a[j][1];
-                const double e0 = exp_nonpos(fma(c, rr0, q0)), e1 = exp_nonpos(fma(c, rr1, q1));
+                const double e0 = exp_nonpos(fma(c, rr0, q0), s_etab), e1 = exp_nonpos(fma(c, rr1, q1), s_etab);
 #pragma unroll
                 for (int s = 0; s < P; ++s) {
                     v0[s] = fma(s_amp[s][j], e0, v0[s]);
@@ -286,8 +290,8 @@ __device__ __forceinline__ void asm_fast_rows(const AsmArgs& g, int q, int w, in
 #pragma unroll
                 for (int s = 0; s < P; ++s) {
                     const double c = s_cs[s][j];
-                    v0[s] = fma(s_amp[s][j], exp_nonpos(fma(c, rr0, q0)), v0[s]);
-                    v1[s] = fma(s_amp[s][j], exp_nonpos(fma(c, rr1, q1)), v1[s]);
+                    v0[s] = fma(s_amp[s][j], exp_nonpos(fma(c, rr0, q0), s_etab), v0[s]);
+                    v1[s] = fma(s_amp[s][j], exp_nonpos(fma(c, rr1, q1), s_etab), v1[s]);
                 }
             }
         }
@@ -320,11 +324,13 @@ __global__ void __launch_bounds__(256, 2) assemble_fast_kernel(const __grid_cons
     __shared__ double s_diag[AGPN_MAXP][ASM_TILE];
     __shared__ __align__(16) double s_rowt[ASMF_MAXQ][2][ASM_TILE];   // sin, cos of b (t_row - t0)
     __shared__ __align__(16) double s_colt[ASMF_MAXQ][2][ASM_TILE];   // sin, cos of b (t_col - t0)
+    __shared__ __align__(128) double s_etab[16];                       // 2^(j/16) for exp_nonpos
 
     const int tid = threadIdx.x;
     const int w = blockIdx.y;
     const int q = S.q;
     const int t = blockIdx.x;
+    if (tid >= 240) s_etab[tid - 240] = c_exp2_16[tid - 240];
     int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
     while (bi * (bi + 1) / 2 > t) --bi;
@@ -389,9 +395,9 @@ __global__ void __launch_bounds__(256, 2) assemble_fast_kernel(const __grid_cons
     for (int s = 0; s < P; ++s) chk[s] = 0.0;
     const bool edge = (bi == bj) || (i0 + ASM_TILE > g.na) || (j0 + ASM_TILE > g.nb);
     if (edge)
-        asm_fast_rows<P, WSE, true>(g, q, w, bi, bj, i0, j0, s_a, s_amp, s_cs, s_rowt, s_colt, s_ta, s_tb, s_diag, chk);
+        asm_fast_rows<P, WSE, true>(g, q, w, bi, bj, i0, j0, s_a, s_amp, s_cs, s_rowt, s_colt, s_ta, s_tb, s_diag, s_etab, chk);
     else
-        asm_fast_rows<P, WSE, false>(g, q, w, bi, bj, i0, j0, s_a, s_amp, s_cs, s_rowt, s_colt, s_ta, s_tb, s_diag, chk);
+        asm_fast_rows<P, WSE, false>(g, q, w, bi, bj, i0, j0, s_a, s_amp, s_cs, s_rowt, s_colt, s_ta, s_tb, s_diag, s_etab, chk);
     if (g.kflag != nullptr) {
 #pragma unroll
         for (int s = 0; s < P; ++s)

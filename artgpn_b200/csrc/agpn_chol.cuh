@@ -57,11 +57,34 @@ struct CholArgs {
     int sgroup = 0;             // block columns the slice storage of one matrix holds
     int keep_factor = 0;        // 1: the FP64 panels of L are stored even when only the digit planes are read again
     int* i8flag = nullptr;      // [nmat] or nullptr: set when a panel entry exceeds its row scale (digits would wrap)
+    // ill-conditioned diagonal blocks: potrf_diag_kernel sets refine[mat] when max L_jj > refine_ratio * min L_jj for the
+    // block it has just factorised; trsm_kernel then solves that block column by substitution (backward stable, like
+    // LAPACK's dtrsm) instead of multiplying by the explicit inverse (whose error grows with cond(L_kk))
+    int* refine = nullptr;      // [nmat][refine_blocks] or nullptr
+    int refine_blocks = 1;      // 1: one flag per matrix, rewritten every block column (launch-ordered chain); nblk: one per
+                                // diagonal block (the persistent task kernel, where panel solves of column k may still run
+                                // when diagonal block k + 1 is factorised -- Linv is then kept per column too, linv_blocks = nblk)
+    double refine_ratio = 1.0e3;
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Thread groups of 256: the FP64 bodies below (operand pipeline, panel solve, diagonal block) are written for 256
+// threads.  In a 256-thread CTA the group is the CTA; the persistent task kernel (agpn_mega.cuh) runs 512-thread CTAs in
+// which the two halves work on two tiles at once, each with its own named barrier.
+// (G = false: plain 256-thread CTA, everything below compiles to what it was without groups)
+template <bool G>
+__device__ __forceinline__ int grp_tid() { return G ? (int)(threadIdx.x & 255u) : (int)threadIdx.x; }
+template <bool G>
+__device__ __forceinline__ int grp_id() { return G ? (int)(threadIdx.x >> 8) : 0; }
+template <bool G>
+__device__ __forceinline__ void grp_sync() {
+    if (!G) __syncthreads();
+    else if (threadIdx.x < 256) asm volatile("bar.sync 3, 256;\n" ::: "memory");
+    else asm volatile("bar.sync 4, 256;\n" ::: "memory");
 }
 
 // ---- digit planes of the INT8-sliced trailing update (agpn_i8.cuh) ---------------------------------------------
@@ -221,12 +244,13 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
 }
 
 // call once per kernel by all 256 threads, before the first GEMM; bars = 2 * GEMM_STAGES uint64_t in shared
+template <bool G = false>
 __device__ __forceinline__ GemmPipe gemm_pipe_init(unsigned long long* bars) {
     GemmPipe p;
     p.full = (unsigned)__cvta_generic_to_shared(bars);
     p.empty = p.full + 8 * GEMM_STAGES;
     p.g = 0;
-    if (threadIdx.x == 0) {
+    if (grp_tid<G>() == 0) {
 #pragma unroll
         for (int s = 0; s < GEMM_STAGES; ++s) {
             mbar_init(p.full + 8 * s, 256);
@@ -234,7 +258,7 @@ __device__ __forceinline__ GemmPipe gemm_pipe_init(unsigned long long* bars) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    __syncthreads();
+    grp_sync<G>();
     return p;
 }
 
@@ -255,9 +279,10 @@ __device__ __forceinline__ void gemm_issue_chunk(const GemmPipe& p, int c, const
 // returns, every cp.async issued by ANY thread of the CTA for this GEMM has completed (the last
 // full-barrier needs all 256 arrivals), so global operands may be overwritten; shared memory may
 // still be read by slower warps -- callers that reuse it by other means need their own barrier.
+template <bool G = false>
 __device__ __forceinline__ void gemm_nt_prologue(const GemmPipe& p, const double* __restrict__ Ag, int lda,
                                                  const double* __restrict__ Bg, int ldb, int K, double* smem) {
-    const int tid = threadIdx.x;
+    const int tid = grp_tid<G>();
     const int nch = K / GEMM_KC;
 #pragma unroll
     for (int c = 0; c < GEMM_STAGES - 1; ++c)
@@ -266,10 +291,11 @@ __device__ __forceinline__ void gemm_nt_prologue(const GemmPipe& p, const double
 
 // kc_limit: this warp's operand columns are exactly zero from k-chunk kc_limit on (triangular B): it skips the tensor
 // work of those chunks but still takes part in the loads and the barriers.
+template <bool G = false>
 __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __restrict__ Ag, int lda,
                                                  const double* __restrict__ Bg, int ldb, int K, double (&acc)[4][4][2],
                                                  double* smem, bool active = true, int kc_limit = 1 << 30) {
-    const int tid = threadIdx.x;
+    const int tid = grp_tid<G>();
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int wm = warp >> 1;
@@ -297,11 +323,12 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __re
     p.g += nch;
 }
 
+template <bool G = false>
 __device__ __forceinline__ void gemm_nt_tile(GemmPipe& p, const double* __restrict__ Ag, int lda, const double* __restrict__ Bg,
                                              int ldb, int K, double (&acc)[4][4][2], double* smem, bool active = true,
                                              int kc_limit = 1 << 30) {
-    gemm_nt_prologue(p, Ag, lda, Bg, ldb, K, smem);
-    gemm_nt_mainloop(p, Ag, lda, Bg, ldb, K, acc, smem, active, kc_limit);
+    gemm_nt_prologue<G>(p, Ag, lda, Bg, ldb, K, smem);
+    gemm_nt_mainloop<G>(p, Ag, lda, Bg, ldb, K, acc, smem, active, kc_limit);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -337,7 +364,7 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
     const double* Aj = A + ((size_t)tj * TB + h * BN) * ld + (size_t)kfirst * TB;
     double* C = A + (size_t)ti * TB * ld + (size_t)tj * TB + h * BN;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     // right half of a diagonal tile: rows 0..63 lie strictly above the diagonal, never read
     const bool active = !(bi == bj && h == 1 && wm < 2);
@@ -383,26 +410,62 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
 // storage's group) -- digits are staged in the idle pipeline buffers in the tensor core's operand layout and leave
 // as two contiguous 32 KB blocks per half;  bit 1: do not store the FP64 panel (nothing reads it when every later
 // update runs on the digit planes).
-__global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0, int flags) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ double zs[TB];
-    __shared__ double qs[TB];                  // Q / r_i of this row tile (digit planes)
-    __shared__ double red[2][TB];
-    __shared__ __align__(8) unsigned long long bars[2 * GEMM_STAGES];
-    GemmPipe pipe = gemm_pipe_init(bars);
-    const int ti = k + 1 + blockIdx.x;
-    const int mat = blockIdx.y;
+// body of the panel solve for tile (ti, k) of matrix `mat`: all 256 threads of the CTA; `smem` = GEMM_SMEM_BYTES of
+// dynamic shared memory, `pipe` = the CTA's operand pipeline (its chunk counter runs on across calls)
+template <bool G = false>
+__device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int flags, int ti, int mat, double* smem, GemmPipe& pipe) {
+    __shared__ double zs_[G ? 2 : 1][TB];
+    __shared__ double qs_[G ? 2 : 1][TB];      // Q / r_i of this row tile (digit planes)
+    __shared__ double red_[G ? 2 : 1][2][TB];
+    double* zs = zs_[grp_id<G>()];
+    double* qs = qs_[grp_id<G>()];
+    double (*red)[TB] = red_[grp_id<G>()];
     double* A = g.A + (size_t)mat * g.mat_stride;
     const int ld = g.ld;
     double* Aik = A + (size_t)ti * TB * ld + (size_t)k * TB;
     const double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
     double* rhs = g.rhs ? g.rhs + (size_t)mat * ((size_t)g.nblk * TB) : nullptr;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = grp_tid<G>(), lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     if (rhs != nullptr && tid < TB) zs[tid] = rhs[(size_t)k * TB + tid];
     if ((flags & 1) && tid >= TB) qs[tid - TB] = g.rscale[(size_t)mat * 2 * ((size_t)g.nblk * TB) + (size_t)ti * TB + tid - TB];
-    __syncthreads();
+    // ill-conditioned diagonal block (flag set by potrf_diag_kernel): X L_kk^T = A_ik by substitution, in place, one
+    // thread per row, 16 columns at a time in registers; L_kk sits packed (lower triangle) in the pipeline buffers
+    const bool refine = g.refine != nullptr && g.refine[(size_t)mat * g.refine_blocks + (g.refine_blocks > 1 ? k : 0)] != 0;   // CTA-uniform
+    if (refine) {
+        const double* Lkk = A + (size_t)k * TB * ld + (size_t)k * TB;
+        for (int idx = tid; idx < TB * TB; idx += 256) {
+            const int i = idx >> 7, j = idx & (TB - 1);
+            if (j <= i) smem[i * (i + 1) / 2 + j] = Lkk[(size_t)i * ld + j];
+        }
+        grp_sync<G>();
+        if (tid < TB) {
+            double* xr = Aik + (size_t)tid * ld;
+#pragma unroll 1
+            for (int b = 0; b < TB / 16; ++b) {
+                double x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = xr[16 * b + j];
+#pragma unroll 1
+                for (int m = 0; m < 16 * b; ++m) {
+                    const double xm = xr[m];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = fma(-xm, smem[(16 * b + j) * (16 * b + j + 1) / 2 + m], x[j]);
+                }
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int gm = 16 * b + m;
+                    x[m] = x[m] / smem[gm * (gm + 1) / 2 + gm];
+#pragma unroll
+                    for (int j = m + 1; j < 16; ++j) x[j] = fma(-x[m], smem[(16 * b + j) * (16 * b + j + 1) / 2 + gm], x[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) xr[16 * b + j] = x[j];
+            }
+        }
+    }
+    grp_sync<G>();
     double part[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][4][2];
 #pragma unroll
@@ -414,7 +477,20 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
             for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
         // rows h * 64 + wn * 32 .. + 31 of the (lower triangular) inverse are zero right of column h * 64 + wn * 32 + 31:
         // the wn = 0 warps stop 32 columns (two k-chunks) early
-        gemm_nt_tile(pipe, Aik, ld, Linv + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem, true,
+        if (refine) {
+            // the panel has been solved in place above: fetch this half in accumulator layout
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int row = wm * 32 + mi * 8 + (lane >> 2);
+                    const int col = h * BN + wn * 32 + ni * 8 + 2 * (lane & 3);
+                    const double2 v = *reinterpret_cast<const double2*>(Aik + (size_t)row * ld + col);
+                    acc[mi][ni][0] = v.x;
+                    acc[mi][ni][1] = v.y;
+                }
+        } else
+        gemm_nt_tile<G>(pipe, Aik, ld, Linv + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem, true,
                      (h * BN + wn * 32 + 32) / GEMM_KC);
         // every load of this GEMM (by any thread) has completed: the in-place store is safe
 #pragma unroll
@@ -423,14 +499,14 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
             for (int ni = 0; ni < 4; ++ni) {
                 const int row = wm * 32 + mi * 8 + (lane >> 2);
                 const int col = h * BN + wn * 32 + ni * 8 + 2 * (lane & 3);
-                if (!(flags & 2)) *reinterpret_cast<double2*>(Aik + (size_t)row * ld + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                if (!(flags & 2) && !refine) *reinterpret_cast<double2*>(Aik + (size_t)row * ld + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
                 if (rhs != nullptr) {
                     part[mi] = fma(acc[mi][ni][0], zs[col], part[mi]);
                     part[mi] = fma(acc[mi][ni][1], zs[col + 1], part[mi]);
                 }
             }
         if (flags & 1) {
-            __syncthreads();                                       // slower warps may still read the last operand stages
+            grp_sync<G>();                                       // slower warps may still read the last operand stages
             unsigned char* stg = reinterpret_cast<unsigned char*>(smem);      // [wn = 32-column chunk][slice][4096]
             int wrapped = 0;
 #pragma unroll
@@ -449,7 +525,7 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
                 }
             }
             if (wrapped && g.i8flag != nullptr) atomicOr(g.i8flag + mat, 1);
-            __syncthreads();
+            grp_sync<G>();
             signed char* S = g.S8 + (size_t)mat * i8_slices_per_matrix(g.nblk, g.sgroup);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -458,7 +534,7 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
 #pragma unroll
                 for (int i = 0; i < I8_TILE_BYTES / 16 / 256; ++i) dstg[i * 256 + tid] = src[i * 256 + tid];
             }
-            __syncthreads();                                       // the next pass refills the pipeline buffers
+            grp_sync<G>();                                       // the next pass refills the pipeline buffers
         }
     }
     if (rhs != nullptr) {
@@ -469,9 +545,16 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             if ((lane & 3) == 0) red[wn][wm * 32 + mi * 8 + (lane >> 2)] = s;
         }
-        __syncthreads();
+        grp_sync<G>();
         if (tid < TB) rhs[(size_t)ti * TB + tid] -= red[0][tid] + red[1][tid];
     }
+}
+
+__global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0, int flags) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * GEMM_STAGES];
+    GemmPipe pipe = gemm_pipe_init(bars);
+    trsm_body(g, k, k0, flags, k + 1 + (int)blockIdx.x, (int)blockIdx.y, smem, pipe);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -560,8 +643,9 @@ __device__ __forceinline__ void potrf_block_update(double* S, int r0, int q0, in
                 make_double2(acc[mi][ni][0], acc[mi][ni][1]);
 }
 
-__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
-    extern __shared__ __align__(16) double smem[];
+// body for the diagonal block k of matrix `mat`: all 256 threads of the CTA, `smem` = POTRF_SMEM_BYTES
+template <bool G = false>
+__device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int mat, double* smem) {
     double* S = smem;                          // [128][132]: lower = A -> L ; strict upper = Linv^T
     double* invd = S + TB * PD_LD;             // [128] 1 / L_jj
     double* zs = invd + TB;                    // [128] rhs block
@@ -569,9 +653,9 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
     double* Dv = zout + TB;                    // [8][16][20] diagonal 16 x 16 inverses (full squares)
     double* scr = Dv + 8 * 16 * PD_DV_LD;      // [8][16][20] per-warp scratch
     __shared__ int s_fail;
+    __shared__ int s_refine;
 
-    const int mat = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = grp_tid<G>(), lane = tid & 31, warp = tid >> 5;
     const int ld = g.ld;
     double* Akk = g.A + (size_t)mat * g.mat_stride + (size_t)k * TB * ld + (size_t)k * TB;
     double* rhs = g.rhs ? g.rhs + (size_t)mat * ((size_t)g.nblk * TB) + (size_t)k * TB : nullptr;
@@ -600,7 +684,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
         }
     }
     if (rhs != nullptr && tid < TB) zs[tid] = rhs[tid];
-    __syncthreads();
+    grp_sync<G>();
 
     // ---- factor: panels of 16 columns; the diagonal block of panel pb+1 (serial, one warp) is
     //      factorised while the other warps apply panel pb to the rest of the trailing matrix --------
@@ -611,7 +695,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
     for (int pb = 0; pb < 8; ++pb) {
 #endif
         const int c0 = pb * 16;
-        __syncthreads();
+        grp_sync<G>();
         // B: rows below the diagonal block, one thread per row: x L_D^T = b
         const int nrows = TB - c0 - 16;
         if (tid < nrows) {
@@ -630,7 +714,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) rowp[j] = x[j];
         }
-        __syncthreads();
+        grp_sync<G>();
         if (pb == 7) break;
         // C: trailing blocks (bi >= bj > pb) -= X_bi X_bj^T
         const int nb = 7 - pb;
@@ -647,6 +731,27 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
                 const int bj = t - bi * (bi + 1) / 2;
                 potrf_block_update(S, (pb + 1 + bi) * 16, (pb + 1 + bj) * 16, c0, lane);
             }
+        }
+    }
+
+    // ---- conditioning of the block: max L_jj / min L_jj (a lower bound of cond(L_kk)) decides whether the panel solve
+    //      multiplies by the explicit inverse (error ~ eps cond(L_kk)) or substitutes (see CholArgs::refine) ----------
+    if (warp == 0) {
+        double mx = 0.0, mn = 1.0e300;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double v = invd[lane + 32 * u];            // 1 / L_jj
+            mx = fmax(mx, v);
+            mn = fmin(mn, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if (lane == 0) {
+            s_refine = (g.refine != nullptr && !(mx <= g.refine_ratio * mn)) ? 1 : 0;
+            if (g.refine != nullptr) g.refine[(size_t)mat * g.refine_blocks + (g.refine_blocks > 1 ? k : 0)] = s_refine;
         }
     }
 
@@ -674,7 +779,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
             for (int i = 0; i < 16; ++i) Dv[warp * 16 * PD_DV_LD + i * PD_DV_LD + c] = x[i];
         }
     }
-    __syncthreads();
+    grp_sync<G>();
     // ---- inverse, step 2: warp j owns block column j of X = L^-1 and walks down the block rows:
     //      X_ij = -Dinv_i * sum_{m=j}^{i-1} L_im X_mj.  No block-wide barrier: a warp only reads
     //      the X blocks it produced itself.  Four accumulator sets keep the DMMA chains short. -------
@@ -752,7 +857,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
             __syncwarp();
         }
     }
-    __syncthreads();
+    grp_sync<G>();
 
     // ---- write the inverse (full tile, zeros above the diagonal) -------------------------------------
     double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
@@ -765,7 +870,20 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
     }
 
     // ---- z_k = Linv r_k ; |z_k|^2 ; sum log L_jj ------------------------------------------------------
-    if (rhs != nullptr) {
+    if (rhs != nullptr && s_refine) {
+        // ill-conditioned block: forward substitution on L itself (lower triangle of S), column by column
+        for (int m = 0; m < TB; ++m) {
+            if (tid == m) zs[m] = zs[m] / S[m * PD_LD + m];
+            grp_sync<G>();
+            if (tid > m && tid < TB) zs[tid] = fma(-S[tid * PD_LD + m], zs[m], zs[tid]);
+            grp_sync<G>();
+        }
+        if (tid < TB) {
+            zout[tid] = zs[tid];
+            rhs[tid] = zs[tid];
+        }
+        grp_sync<G>();
+    } else if (rhs != nullptr) {
         if (tid < TB) {
             const int R = tid;
             const int b0 = (R >> 4) * 16;
@@ -775,7 +893,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
             zout[R] = sacc;
             rhs[R] = sacc;
         }
-        __syncthreads();
+        grp_sync<G>();
     }
     if (tid < 32) {
         double qv = 0.0, lv = 0.0;
@@ -799,4 +917,9 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
             if (s_fail && g.info[mat] == 0) g.info[mat] = 1;
         }
     }
+}
+
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(CholArgs g, int k) {
+    extern __shared__ __align__(16) double smem[];
+    potrf_diag_body(g, k, (int)blockIdx.x, smem);
 }

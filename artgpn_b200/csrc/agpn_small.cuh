@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(256) small_fused_kernel(const __grid_constant_
     __shared__ double s_fa[AGPN_MAXQ][3];        // fast path: a_j, c_j + cw_j, amp
     __shared__ RKern s_rnode[AGPN_MAXQ], s_rweight[AGPN_MAXQ];
     __shared__ int s_fail, s_bad;
+    __shared__ __align__(128) double s_etab[16];   // 2^(j/16) for exp_nonpos
 
     const int series = blockIdx.x, w = blockIdx.y;
     const int mat = w * S.p + series;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) small_fused_kernel(const __grid_constant_
     const double* th = g.theta + (size_t)w * S.D;
 
     if (tid == 0) { s_fail = 0; s_bad = 0; }
+    if (tid >= 240) s_etab[tid - 240] = c_exp2_16[tid - 240];
     if (tid < q) {
         const PKern kn = prep_kernel(0, S.node_kind[tid], th + S.node_off[tid]);
         const int widx = tid + q * series;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(256) small_fused_kernel(const __grid_constant_
                     for (int j = 0; j < q; ++j) {
                         const double sn = fma(trig[(2 * j) * np + gi], trig[(2 * j + 1) * np + gj],
                                               -trig[(2 * j + 1) * np + gi] * trig[(2 * j) * np + gj]);
-                        v = fma(s_fa[j][2], exp_nonpos(fma(s_fa[j][1], r2, s_fa[j][0] * sn * sn)), v);
+                        v = fma(s_fa[j][2], exp_nonpos(fma(s_fa[j][1], r2, s_fa[j][0] * sn * sn), s_etab), v);
                     }
                 } else if (g.exact) {
                     const bool dg = gi == gj;

@@ -238,6 +238,14 @@ int agpn_update_path(const agpn_ctx* ctx);
  * fall-back when an entry of K* L^-T exceeds its row scale sqrt(k**_ii)), -1 = no prediction yet. */
 int agpn_predict_path(const agpn_ctx* ctx);
 int agpn_slice_ms(agpn_ctx* ctx, double* ms, long long* launches);
+/* Diagnostics (context created with AGPN_TIMELINE=1 in the environment): CSV of start / end times, phase and sub-batch
+ * stream of every launch of the last agpn_loglike_batch, measured WITHOUT serialising the streams. */
+int agpn_timeline_dump(agpn_ctx* ctx, const char* path);
+/* Diagnostics (AGPN_MEGA_PROF=1): per-CTA means of the persistent task kernel's time slots of the last wave, in
+ * microseconds (slots 1, 4, 7 are task counts): 0 update runs, 1 update tasks, 2 diagonal-block bodies, 3 their waits,
+ * 4 diagonal-block tasks, 5 panel-solve bodies, 6 their waits, 7 panel-solve tasks (thread group 0), 8 whole kernel,
+ * 9 cluster syncs before update runs, 10 producer waits for panels. */
+int agpn_mega_prof(agpn_ctx* ctx, double* out16);
 
 #ifdef __cplusplus
 }

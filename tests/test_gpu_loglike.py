@@ -169,3 +169,61 @@ def test_sharded_entry_point_single_rank_nccl():
         assert full.is_cuda and H.rel_err(full.cpu().numpy(), exp) <= LL_RTOL
     finally:
         dist.destroy_process_group()
+
+
+# ---- ill-conditioned covariances (tests/golden/make_golden_cond.py: the reference on synth512 with the noise terms
+#      scaled down; cond(K) from 7e3 to 7e11) ---------------------------------------------------------------------
+def _cond_goldens():
+    import json
+    import os
+    with open(os.path.join(H.GOLD, "golden_cond.json")) as f:
+        g = json.load(f)
+    return g, dict(np.load(os.path.join(H.GOLD, "golden_cond.npz")))
+
+
+# The log-likelihood of an ill-conditioned block moves by ~cond(K) * d for a relative change d of the covariance
+# entries, and the reference's own entries carry last-ulp (libm) and argument-rounding noise: two correct
+# implementations agree to ~cond(K) * eps at best.  Bound: max(1e-9, 50 cond eps) -- the 1e-9 of the north_star holds
+# up to cond ~ 1e5 / eps * 1e-9 ~ 1e5..1e6, beyond that parity degrades linearly in cond, for any implementation.
+COND_FACTOR = 50.0
+
+
+@pytest.mark.parametrize("mode", ["i8", "dmma"])
+@pytest.mark.parametrize("exact", [False, True], ids=["default", "exact"])
+@pytest.mark.parametrize("k", range(7))
+def test_ill_conditioned_goldens(monkeypatch, k, exact, mode):
+    from artgpn_b200 import synth, node, weight, mean
+    from artgpn_b200.arttwo import network
+    g, a = _cond_goldens()
+    c = g["cases"][k]
+    p, q = g["p"], g["q"]
+    monkeypatch.setenv("AGPN_SYRK", mode)
+    args = []
+    for i in range(p):
+        args += [a["y"][i], a["yerr"][i] * c["scale"]]
+    net = network(q, a["time"], *args, exact=exact)
+    got = net.log_likelihood(*synth.objects_from_row(node, weight, mean, a["theta_%d" % k], p, q, g["weights"]))
+    net.close()
+    # positive definite in LAPACK (the reference returned a finite value) => positive definite here
+    assert np.isfinite(got), (c["name"], got)
+    cond = max(c["cond"])
+    bound = max(LL_RTOL, COND_FACTOR * cond * np.finfo(float).eps)
+    assert abs(got - c["ll"]) <= bound * abs(c["ll"]), (c["name"], mode, exact, abs(got - c["ll"]) / abs(c["ll"]), bound)
+
+
+@pytest.mark.parametrize("mode", ["i8", "dmma"])
+def test_substitution_panel_solve_matches_goldens(monkeypatch, mode):
+    """AGPN_REFINE_RATIO=0 sends EVERY block column through the substitution panel solve (normally taken only for
+    ill-conditioned diagonal blocks): same log-likelihoods as the reference on the well-conditioned batch goldens."""
+    from artgpn_b200 import synth, node, weight, mean
+    monkeypatch.setenv("AGPN_SYRK", mode)
+    monkeypatch.setenv("AGPN_REFINE_RATIO", "0")
+    monkeypatch.setenv("AGPN_NO_SMALL", "1")
+    for b in H.cases()["batch"]:
+        a = H.arrays()
+        theta, exp = a[b["name"] + "_theta"], a[b["name"] + "_ll"]
+        net = H.product_network(b["data"], b["q"])
+        net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], b["p"], b["q"], b["weights"])[:3])
+        got = net.log_likelihood_batch(theta)
+        assert H.rel_err(got, exp) <= LL_RTOL, (b["name"], got, exp)
+        net.close()

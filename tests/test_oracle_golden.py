@@ -121,3 +121,23 @@ def test_covariance_blocks_match_reference(cc):
                        a[key + "_compute_nugget_shift"], rtol=1e-13, atol=1e-13)
     assert np.allclose(oracle.mean_vector(means, d["time"], p).reshape(-1), a[key + "_meanvec"], rtol=1e-13, atol=1e-10)
     assert np.allclose(oracle.mean_vector(means, tg, p).reshape(-1), a[key + "_meanvec_grid33"], rtol=1e-13, atol=1e-10)
+
+
+def test_oracle_matches_reference_on_ill_conditioned_goldens():
+    """tests/golden/make_golden_cond.py: the oracle performs the reference's numpy / LAPACK operations in the
+    reference's order, so it reproduces the reference even where cond(K) ~ 1e11 amplifies every rounding."""
+    import json
+    import os
+    from artgpn_b200 import synth
+    with open(os.path.join(H.GOLD, "golden_cond.json")) as f:
+        g = json.load(f)
+    a = dict(np.load(os.path.join(H.GOLD, "golden_cond.npz")))
+
+    class M(object):
+        def __getattr__(self, name):
+            return lambda *pars: (name, list(pars))
+    m = M()
+    for k, c in enumerate(g["cases"]):
+        o = synth.objects_from_row(m, m, m, a["theta_%d" % k], g["p"], g["q"], g["weights"])
+        got = oracle.log_likelihood(a["time"], a["y"], a["yerr"] * c["scale"], g["q"], *o)
+        assert abs(got - c["ll"]) <= 1e-12 * abs(c["ll"]) * max(1.0, max(c["cond"]) * 1e-6), (c["name"], got, c["ll"])
