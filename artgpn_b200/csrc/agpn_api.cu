@@ -167,8 +167,8 @@ struct agpn_ctx {
     bool lookahead_forced = false;     // AGPN_LOOKAHEAD=2: for every batch size (default: few matrices only)
     cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_la[8][2] = {};
-    // persistent tile-task kernel (agpn_mega.cuh): one launch per wave instead of the per-column chain (AGPN_MEGA=0 disables)
-    bool use_mega = true;
+    // persistent tile-task kernel (agpn_mega.cuh): one launch per wave instead of the per-column chain; opt-in
+    bool use_mega = false;         // AGPN_MEGA=1 enables it (measured: 23.9 vs 21.1 ms at 128 walkers, 3.66 vs 3.24 ms at 16)
     int* d_mega = nullptr;         // fD | fP | fU | refine per block, ints
     size_t cap_mega = 0;
     int linv_blocks = 1;           // inverse blocks kept per matrix in d_Linv (nblk with the task kernel)
@@ -657,16 +657,16 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
                     CUDA_TRY(cudaEventRecord(la->fork, st));
                     CUDA_TRY(cudaStreamWaitEvent(la->side, la->fork, 0));
                     const int ncl_d = balanced_clusters(c, g.nmat);
-                    syrk_i8_persistent_kernel<<<2 * ncl_d, I8_THREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, 1, g.nmat, 0);
+                    syrk_i8_persistent_kernel<<<2 * ncl_d, I8_PTHREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, 1, g.nmat, 0);
                     LAUNCH_CHECK();
                     const int ntl = g.nblk - k - 1, total = ntl * g.nmat;
                     const int ncl = balanced_clusters(c, total);
-                    syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, la->side>>>(g, k - k0, k, 1, ntl, total, 1);
+                    syrk_i8_persistent_kernel<<<2 * ncl, I8_PTHREADS, I8_SMEM_BYTES, la->side>>>(g, k - k0, k, 1, ntl, total, 1);
                     CUDA_TRY(cudaEventRecord(la->join, la->side));
                 } else if ((i8 & 1) && c->i8_persist) {
                     const int ntl = g.nblk - k, total = ntl * g.nmat;
                     const int ncl = balanced_clusters(c, total);
-                    syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, ntl, total, 0);
+                    syrk_i8_persistent_kernel<<<2 * ncl, I8_PTHREADS, I8_SMEM_BYTES, st>>>(g, k - k0, k, 1, ntl, total, 0);
                 } else if (i8 & 1)
                     syrk_i8_kernel<<<dim3(2 * (g.nblk - k), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, k - k0, k, 1);
                 else if (c->maps_valid && (c->tma_which & 1))
@@ -706,7 +706,7 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
             if ((i8 & 2) && c->i8_persist) {
                 const int ntl = nt * (nt + 1) / 2, total = ntl * g.nmat;
                 const int ncl = balanced_clusters(c, total);
-                syrk_i8_persistent_kernel<<<2 * ncl, I8_THREADS, I8_SMEM_BYTES, st>>>(g, kend - k0, kend, 0, ntl, total, 0);
+                syrk_i8_persistent_kernel<<<2 * ncl, I8_PTHREADS, I8_SMEM_BYTES, st>>>(g, kend - k0, kend, 0, ntl, total, 0);
             } else if (i8 & 2)
                 syrk_i8_kernel<<<dim3(nt * (nt + 1), g.nmat), I8_THREADS, I8_SMEM_BYTES, st>>>(g, k0, kend - k0, kend, 0);
             else if (c->maps_valid && (c->tma_which & 2))

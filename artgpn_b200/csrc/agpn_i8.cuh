@@ -23,8 +23,8 @@
 // so a stage is filled by plain 1-D bulk copies (cp.async.bulk, no tensor map): 32 KB of A (all 8 slices of 128
 // rows, contiguous) and 8 x 2 KB of B.  The two CTAs that own the left / right 64 columns of a 128 x 128 tile form a
 // cluster and need the same A: each fetches half of it and multicasts it to both (L2 -> SM bytes per CTA and K step:
-// 32 instead of 48 KB).  3 stages x 48 KB; warp 0 = producer, warp 1 = MMA issuer, warps 2..5 = epilogue
-// (TMEM lane quarter = warp % 4); tcgen05.commit (multicast to both CTAs' `empty` barriers) hands stages back.
+// 32 instead of 48 KB).  3 stages x 48 KB; warp 0 = producer, warp 1 = MMA issuer, warps 2.. = epilogue
+// (TMEM lane quarter = warp % 4; the persistent kernel runs eight: two per quarter, each half of the 64 columns); tcgen05.commit (multicast to both CTAs' `empty` barriers) hands stages back.
 // The C tile travels by bulk copies too: every epilogue thread fetches ITS row (512 contiguous bytes) into a
 // padded shared-memory tile before the main loop starts, folds the eight integer diagonals of that row into it
 // after the last MMA and sends the row back with one bulk store -- no thread-per-row strided global access, no
@@ -47,7 +47,11 @@
 #define I8_STAGE_BYTES (I8_NSL * (I8_A_BYTES + I8_B_BYTES))      // 49152
 #define I8_CROW_BYTES (BN * 8 + 16)                              // padded C row: 16-byte accesses of a warp, one row per lane, conflict free
 #define I8_SMEM_BYTES (I8_STAGES * I8_STAGE_BYTES + TB * I8_CROW_BYTES + 1024)   // + slack for 1024-byte alignment
-#define I8_THREADS 192
+#define I8_THREADS 192                                           // per-tile kernel, peak probe
+#ifndef I8_EPW
+#define I8_EPW 8                                                 // epilogue warps of the persistent kernel: 4 or 8 (two per TMEM lane quarter)
+#endif
+#define I8_PTHREADS (64 + 32 * I8_EPW)
 #ifndef I8_PREFETCH
 #define I8_PREFETCH 0
 #endif
@@ -414,7 +418,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_PTHREADS, 1)
 syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles, int total, int bi0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2 * I8_STAGES + 3];
@@ -440,7 +444,7 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
         }
         mbar_init(done, 1);
         mbar_init(cfull, 1);
-        mbar_init(tfree, 4);                                        // one arrival per epilogue warp
+        mbar_init(tfree, I8_EPW);                                   // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -531,10 +535,13 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
         }
     } else {
         // ---------------- epilogue: thread = one row of the tile (TMEM lane) ----------------
-        const int q = warp & 3;
+        const int q = warp & 3;                                     // TMEM lane quarter of this warp
         const int row = q * 32 + lane;
-        const int et = tid - 64;                                    // 0 .. 127 among the epilogue threads
-        const unsigned crow = cs + row * I8_CROW_BYTES;
+        const int et = tid - 64;                                    // 0 .. 32 I8_EPW - 1 among the epilogue threads
+        constexpr int NCH = I8_EPW / 4;                             // warps per lane quarter: each takes BN / NCH columns of the row
+        constexpr int CW = BN / NCH;
+        const int ch = (warp - 2) >> 2;
+        const unsigned crow = cs + row * I8_CROW_BYTES + ch * (CW * 8);
         double* cgen = reinterpret_cast<double*>(smem_raw + (crow - sraw));
         const unsigned tlane = tmem + ((unsigned)(q * 32) << 16);
         unsigned tile = 0;
@@ -545,24 +552,25 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
             const bool half_tile = diag && h == 1;                  // rows 0..63 lie strictly above the diagonal
             const bool skip = half_tile && q < 2;                   // warp-uniform
             const double* esc = g.rscale + (size_t)mat * 2 * n + n;
-            double* Crow = g.A + (size_t)mat * g.mat_stride + (size_t)(ti * TB + row) * g.ld + (size_t)tj * TB + h * BN;
+            double* Crow = g.A + (size_t)mat * g.mat_stride + (size_t)(ti * TB + row) * g.ld + (size_t)tj * TB + h * BN + ch * CW;
             const int eb = tile & 1;
             if (et < BN) ecol[eb][et] = 0.5 * esc[tj * TB + h * BN + et];
             if (et == 0) mbar_expect_tx(cfull, (half_tile ? TB / 2 : TB) * BN * 8);
-            if (!skip) bulk_g2s(crow, Crow, BN * 8, cfull);
+            if (!skip) bulk_g2s(crow, Crow, CW * 8, cfull);
             const double ei = esc[ti * TB + row];
-            named_bar_sync(1, 128);                                 // ecol[eb] visible to the four epilogue warps
+            named_bar_sync(1, 32 * I8_EPW);                         // ecol[eb] visible to all epilogue warps
             mbar_wait(done, tile & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             mbar_wait(cfull, tile & 1);                             // every epilogue thread: nobody may post the next tile's bytes into this phase
             if (!skip) {
 #pragma unroll 1
-                for (int c8 = 0; c8 < BN / 8; ++c8) {
+                for (int c8 = 0; c8 < CW / 8; ++c8) {
+                    const int cc0 = ch * CW + c8 * 8;               // first of these eight columns inside the CTA's 64
                     int v[I8_NSL][8];
 #pragma unroll
-                    for (int d = 0; d < I8_NSL; ++d) tmem_ld8(tlane + d * BN + c8 * 8, v[d]);
+                    for (int d = 0; d < I8_NSL; ++d) tmem_ld8(tlane + d * BN + cc0, v[d]);
                     tmem_ld_wait();
-                    if (c8 == BN / 8 - 1) {                         // last read of the accumulators: hand TMEM back
+                    if (c8 == CW / 8 - 1) {                         // last read of the accumulators: hand TMEM back
                         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tfree);
@@ -577,7 +585,7 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
                             const double H = i8_fold4(v[0][j], v[1][j], v[2][j], v[3][j]);
                             const double Lo = i8_fold4(v[4][j], v[5][j], v[6][j], v[7][j]);
                             const double val = fma(H, 268435456.0, Lo);
-                            r2[u] = (val * ei) * ecol[eb][c8 * 8 + j];
+                            r2[u] = (val * ei) * ecol[eb][cc0 + j];
                         }
                         cc.x -= r2[0];
                         cc.y -= r2[1];
@@ -585,7 +593,7 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                bulk_s2g(Crow, crow, BN * 8);
+                bulk_s2g(Crow, crow, CW * 8);
                 asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");       // the row buffer is free for the next tile's load
             } else {
