@@ -34,6 +34,7 @@ _SIGNATURES = {
     "agpn_comm_rank": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "agpn_loglike_batch_sharded": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, ctypes.c_int, c_void_p,
                                                   ctypes.c_int, c_void_p, c_void_p]),
+    "agpn_loglike_grad": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agpn_covariance_block": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, c_void_p, ctypes.c_int,
                                              c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
                                              ctypes.c_int, c_void_p]),

@@ -340,6 +340,25 @@ class network(object):
             raise ValueError("array must not contain infs or NaNs")
         return float(out[0])
 
+    def log_likelihood_grad(self, nodes, weights, means, jitters):
+        """
+        Log likelihood AND its analytic gradient with respect to every hyper-parameter (not in the reference, which
+        only carries derivative kernel classes: weight.py:81-931).  Returns (ll, grad) with grad in theta-row order:
+        node .pars | weight .pars (list order j + q*i) | mean terms | jitters -- ``Structure.pack`` of the same
+        objects gives the matching parameter vector.  Supported classes: see agpn_loglike_grad.
+        """
+        s = Structure(self.p, self.q, nodes, weights, means)
+        self._apply_structure(s)
+        theta = s.pack(nodes, weights, means, jitters)
+        ll = np.zeros(1)
+        grad = np.zeros(s.D)
+        status = np.zeros(1, dtype=np.int32)
+        _lib.check(_lib.load().agpn_loglike_grad(self._ctx(), _lib.ptr(theta), _lib.ptr(ll), _lib.ptr(grad),
+                                                 _lib.ptr(status), None))
+        if status[0] == STATUS_NOT_FINITE:
+            raise ValueError("array must not contain infs or NaNs")
+        return float(ll[0]), grad
+
     def log_likelihood_batch(self, theta, return_status=False):
         """
         Log likelihoods of W parameter rows (walkers) in one device pass.
@@ -454,6 +473,19 @@ class network(object):
         if status[0] == STATUS_NOT_FINITE:
             raise ValueError("array must not contain infs or NaNs")
         return mu, np.sqrt(np.diag(cov)), cov
+
+    def posterior_sample(self, nodes=None, weights=None, means=None, jitters=None, time=None, dataset=1, size=None,
+                         random_state=None):
+        """
+        Draws from the predictive distribution N(y_mean, y_cov) of `prediction_cov` on the grid `time` (what sampling the
+        `y_cov` of arttwo.py:393 would give): the Schur-complement covariance and its factor both come from the batched
+        Cholesky kernels; only the standard-normal numbers are drawn on the host.  Returns [len(time)] (size=None) or
+        [size, len(time)].
+        """
+        mu, _, cov = self.prediction_cov(nodes, weights, means, jitters, time, dataset)
+        t = np.asarray(time, dtype=np.float64)
+        t = t if t.any() else np.asarray(self.time, dtype=np.float64)
+        return self.sample(cov, t, size=size, random_state=random_state) + mu
 
     # ---- profiling hooks used by bench.py -----------------------------------------------------
     def set_profiling(self, enable):

@@ -22,6 +22,7 @@
 #include "agpn_tma.cuh"
 #include "agpn_i8.cuh"
 #include "agpn_mega.cuh"
+#include "agpn_grad.cuh"
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
@@ -1610,6 +1611,100 @@ extern "C" int agpn_predict_cov(agpn_ctx* c, const double* theta, int series, in
     cudaFree(d_cov);
     CUDA_TRY(e);
     if (status) *status = h_flags[1] ? AGPN_STATUS_NOT_FINITE : (h_flags[0] ? AGPN_STATUS_NOT_PD : (h_flags[2] ? AGPN_STATUS_NOT_FINITE : AGPN_STATUS_OK));
+    return 0;
+}
+
+// log-likelihood and its analytic gradient for one theta row (agpn_grad.cuh)
+extern "C" int agpn_loglike_grad(agpn_ctx* c, const double* theta, double* ll_out, double* grad_out, int* status, void* stream) {
+    if (!c || !theta || !ll_out || !grad_out) USAGE_FAIL("agpn_loglike_grad: null pointer");
+    if (!c->has_structure) USAGE_FAIL("agpn_loglike_grad: call agpn_set_structure first");
+    const Structure& S = c->S;
+    if (S.D > GRAD_MAXD) USAGE_FAIL("agpn_loglike_grad: more than 96 parameters per row");
+    for (int j = 0; j < S.q; ++j)
+        if (!grad_shape_supported(S.node_kind[j])) USAGE_FAIL("agpn_loglike_grad: node kernel class without a gradient (supported: Constant, SquaredExponential, Periodic, QuasiPeriodic, Cosine, Exponential, Matern32, Matern52)");
+    for (int i = 0; i < S.p * S.q; ++i)
+        if (!grad_shape_supported(S.weight_kind[i])) USAGE_FAIL("agpn_loglike_grad: weight kernel class without a gradient (supported: Constant, SquaredExponential, Periodic, QuasiPeriodic, Cosine, Exponential, Matern32, Matern52)");
+    if (S.use_means)
+        for (int t = 0; t < S.mean_first[S.p]; ++t)
+            if (!grad_mean_supported(S.mean_kind[t])) USAGE_FAIL("agpn_loglike_grad: mean class without a gradient (supported: Constant, Linear)");
+    ENTER_DEVICE(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = S.D, p = c->p;
+    const size_t npad = (size_t)c->npad, T = 2 * npad;
+    if (ensure_batch_workspace(c, 1, 1)) return 1;
+    if (T * T > c->cap_aug) {
+        cudaFree(c->d_aug);
+        c->d_aug = nullptr;
+        c->cap_aug = 0;
+        CUDA_TRY(cudaMalloc(&c->d_aug, sizeof(double) * T * T));
+        c->cap_aug = T * T;
+    }
+    const int nt64 = (c->N + 63) / 64, ntiles = nt64 * (nt64 + 1) / 2;
+    DevBuf b_rhs, b_th, b_grad, b_part, b_res;
+    CUDA_TRY(b_rhs.alloc(T));
+    CUDA_TRY(b_th.alloc(D));
+    CUDA_TRY(b_grad.alloc(D));
+    CUDA_TRY(b_part.alloc((size_t)ntiles * GRAD_MAXD));
+    CUDA_TRY(b_res.alloc((size_t)p * npad));
+    CUDA_TRY(cudaMemcpyAsync(b_th.p, theta, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(b_grad.p, 0, sizeof(double) * D, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 4 * c->cap_mats, st));
+    int* d_kflag = c->d_info + c->cap_mats;
+    // residuals of all series (arttwo.py:262-264)
+    MeanArgs m;
+    m.theta = b_th.p; m.t = c->d_t; m.n = c->N; m.n_pad = c->npad; m.tmean = c->tmean; m.t0 = c->t0; m.y = c->d_y;
+    m.out = b_res.p; m.series0 = 0; m.nser = p; m.subtract = 1; m.rflag = nullptr;
+    mean_kernel<<<dim3(p, 1), 256, 0, st>>>(S, m);
+    LAUNCH_CHECK();
+    const bool maps_were = c->maps_valid;
+    int st_code = AGPN_STATUS_OK;
+    for (int i = 0; i < p && st_code == AGPN_STATUS_OK; ++i) {
+        // [[K_i + sigma^2 + s^2, .], [I, 0]] with right-hand side [r_i; 0]
+        AsmArgs a;
+        a.theta = b_th.p; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
+        a.yerr = c->d_yerr; a.out = c->d_aug; a.mat_stride = (long long)(T * T); a.ld = (int)T; a.series0 = i; a.nser = 1;
+        a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1; a.use_trig = 1; a.vec2 = 1;
+        a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
+        if (launch_assemble(c, a, 1, st)) return 1;
+        grad_aug_fill_kernel<<<1024, 256, 0, st>>>(c->d_aug, (int)T, c->npad);
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaMemsetAsync(b_rhs.p, 0, sizeof(double) * T, st));
+        CUDA_TRY(cudaMemcpyAsync(b_rhs.p, b_res.p + (size_t)i * npad, sizeof(double) * npad, cudaMemcpyDeviceToDevice, st));
+        CholArgs g;
+        g.A = c->d_aug; g.mat_stride = (long long)(T * T); g.ld = (int)T; g.nblk = (int)(T / TB); g.nmat = 1;
+        g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = b_rhs.p; g.logdet = c->d_logdet; g.quad = c->d_quad; g.info = c->d_info;
+        g.A0 = c->d_aug; g.mat0 = 0;
+        g.refine = c->d_info + 3 * c->cap_mats; g.refine_ratio = c->refine_ratio;
+        c->maps_valid = false;
+        c->group_eff = c->group_fixed ? c->group : 2;
+        const int rc = run_cholesky(c, g, st, nullptr, c->nblk);
+        c->maps_valid = maps_were;
+        if (rc) return 1;
+        GradArgs ga;
+        ga.theta = b_th.p; ga.t = c->d_t; ga.N = c->N; ga.series = i; ga.Kinv_neg = c->d_aug + npad * T + npad; ga.ld = (int)T;
+        ga.alpha_neg = b_rhs.p + npad; ga.tmean = c->tmean; ga.partial = b_part.p;
+        grad_tile_kernel<<<ntiles, 256, 0, st>>>(S, ga);
+        LAUNCH_CHECK();
+        grad_reduce_kernel<<<(D + 63) / 64, 64, 0, st>>>(b_part.p, ntiles, D, b_grad.p);
+        LAUNCH_CHECK();
+        int h_flags[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(&h_flags[0], c->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&h_flags[1], d_kflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_flags[1]) st_code = AGPN_STATUS_NOT_FINITE;
+        else if (h_flags[0]) st_code = AGPN_STATUS_NOT_PD;
+    }
+    double h_ld = 0.0, h_q = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(&h_ld, c->d_logdet, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&h_q, c->d_quad, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(grad_out, b_grad.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (st_code == AGPN_STATUS_OK && !(std::isfinite(h_q) && std::isfinite(h_ld))) st_code = AGPN_STATUS_NOT_FINITE;
+    *ll_out = st_code == AGPN_STATUS_OK ? -0.5 * h_q - h_ld - 0.5 * (double)c->N * p * std::log(2.0 * AGPN_PI)
+                                        : (st_code == AGPN_STATUS_NOT_PD ? -INFINITY : NAN);
+    if (status) *status = st_code;
     return 0;
 }
 

@@ -180,6 +180,18 @@ int agpn_predict_cov(agpn_ctx* ctx, const double* theta, int series, int M, cons
                      double train_jitter, double* mean_out, double* cov_out, int* status, void* stream);
 
 /*
+ * Log-likelihood of one theta row AND its gradient with respect to every entry of the row (SURVEY.md section 8(f):
+ * new capability -- the reference carries derivative kernel classes, weight.py:81-931, several of them wrong, and never
+ * assembles a gradient).  dLL/dtheta = 1/2 sum_i tr((alpha_i alpha_i^T - K_i^-1) dK_i/dtheta), dLL/dphi = alpha_i^T dm_i/dphi;
+ * K_i^-1 and alpha_i come from a partial blocked Cholesky of [[K_i, .], [I, 0]] on the factorisation kernels, the
+ * derivative tiles are generated on the fly from closed forms (artgpn_b200/csrc/agpn_grad.cuh).  Supported classes: node /
+ * weight kernels Constant, SquaredExponential, Periodic, QuasiPeriodic, Cosine, Exponential|Laplacian, Matern32, Matern52;
+ * means Constant, Linear (and None); any other class is a usage error.  theta, ll_out, grad_out[D]: host.
+ * *status as agpn_loglike_batch (ll = -inf / NaN, gradient undefined, when not OK).
+ */
+int agpn_loglike_grad(agpn_ctx* ctx, const double* theta, double* ll_out, double* grad_out, int* status, void* stream);
+
+/*
  * Replaces one kernel object's __call__ (node.py / weight.py): element-wise value on a
  * [rows][cols] lag array r, or on t1[rows] x t2[cols] for Linear / Polynomial (r ignored).
  * Host pointers; runs on `device`.  square_quirk as above (1 iff rows == cols in the reference).

@@ -280,3 +280,21 @@ def test_prediction_slices_see_the_whole_grid_whitenoise_quirk(M):
         assert np.max(np.abs(smu - mu[lo:hi])) <= 1e-11 * np.max(np.abs(mu)), (M, lo, hi)
         assert np.max(np.abs(ssd ** 2 - sd[lo:hi] ** 2)) <= 1e-11 * np.max(sd ** 2), (M, lo, hi)
     net.close()
+
+
+def test_posterior_samples_have_the_predictive_moments():
+    from artgpn_b200 import node, weight, mean
+    net, (t, y, sig) = _net(120, 2, 1, seed=4)
+    nodes = [node.QuasiPeriodic(20.0, 15.0, 0.8)]
+    ws = [weight.Constant(1.5), weight.Constant(0.9)]
+    ms = [mean.Linear(0.01, 0.2), None]
+    jit = [0.6, 0.8]
+    grid = np.linspace(t.min() - 2, t.max() + 2, 90)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mu, sd, cov = net.prediction_cov(nodes, ws, ms, jit, grid, 1)
+        S = net.posterior_sample(nodes, ws, ms, jit, grid, 1, size=20000, random_state=7)
+    assert S.shape == (20000, grid.size)
+    assert np.max(np.abs(S.mean(axis=0) - mu)) <= 5.0 * np.max(sd) / np.sqrt(S.shape[0])
+    C = np.cov(S.T)
+    assert np.max(np.abs(C - cov)) <= 6.0 * np.max(np.diag(cov)) / np.sqrt(S.shape[0])
+    net.close()
