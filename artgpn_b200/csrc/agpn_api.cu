@@ -168,6 +168,9 @@ struct agpn_ctx {
     bool lookahead_forced = false;     // AGPN_LOOKAHEAD=2: for every batch size (default: few matrices only)
     cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_la[8][2] = {};
+    // panel solves with one CTA per 64-column half of a tile (AGPN_TRSM_SPLIT=0: one CTA per tile)
+    bool trsm_split = true;
+    double* d_rslot = nullptr;     // [cap_mats][nblk][2][2][128] parked forward-solve sums of the split panel solves
     // persistent tile-task kernel (agpn_mega.cuh): one launch per wave instead of the per-column chain; opt-in
     bool use_mega = false;         // AGPN_MEGA=1 enables it (measured: 23.9 vs 21.1 ms at 128 walkers, 3.66 vs 3.24 ms at 16)
     int* d_mega = nullptr;         // fD | fP | fU | refine per block, ints
@@ -290,6 +293,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_I8_PERSIST")) c->i8_persist = atoi(e) != 0;
     if (const char* e = getenv("AGPN_I8_BALANCE")) c->i8_balance = atoi(e) != 0;
     if (const char* e = getenv("AGPN_MEGA")) c->use_mega = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_TRSM_SPLIT")) c->trsm_split = atoi(e) != 0;
     if (const char* e = getenv("AGPN_MEGA_PROF")) if (atoi(e) != 0) {
         if (cudaMalloc(&c->d_megaprof, sizeof(unsigned long long) * 16 * 2 * c->i8_clusters_max) != cudaSuccess) { cudaGetLastError(); c->d_megaprof = nullptr; }
     }
@@ -375,7 +379,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_S8); cudaFree(c->d_rscale);
     cudaFree(c->d_paug); cudaFree(c->d_ps8); cudaFree(c->d_pvec);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
-    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof);
+    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot);
     agpn_comm_release(c);
     delete c;
     return 0;
@@ -587,6 +591,10 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_logdet, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 4 * nmat));
+        cudaFree(c->d_rslot);
+        c->d_rslot = nullptr;
+        if (c->trsm_split && c->i8_which == 3 && c->nblk > 2)
+            CUDA_TRY(cudaMalloc(&c->d_rslot, sizeof(double) * nmat * c->nblk * 4 * 128));
         if (mega_eligible(c)) {
             cudaFree(c->d_mega);
             c->d_mega = nullptr;
@@ -690,7 +698,10 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
                 CUDA_TRY(cudaStreamWaitEvent(st, la->join, 0));
             if (k < g.nblk - 1) {
                 PhaseScope ps(c, st, PH_TRSM, cur);
-                trsm_kernel<<<dim3(g.nblk - k - 1, g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k, k0, tflags);
+                // one CTA per 64-column half of a tile when the FP64 panel is not stored (no in-place overwrite to order) and
+                // the forward-solve sums can be parked (g.rslot): half the latency per launch, finer-grained SM packing
+                const bool split = (tflags & 2) && g.rslot != nullptr && g.rhs != nullptr;
+                trsm_kernel<<<dim3((split ? 2 : 1) * (g.nblk - k - 1), g.nmat), 256, GEMM_SMEM_BYTES, st>>>(g, k, k0, tflags | (split ? 8 : 0));
                 LAUNCH_CHECK();
             }
             // digit planes of the new panel, if a later update of this group reads them on the INT8 path
@@ -844,6 +855,10 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         }
         // row scales r_i = sqrt(K_ii) >= |L_ik| from the assembled diagonal, before the factorisation overwrites it
         g.S8 = c->d_S8; g.rscale = c->d_rscale; g.sgroup = c->sgroup;
+        // split panel solves: on the pure INT8 likelihood path every panel solve of the wave leaves its FP64 panel unstored,
+        // so every launch can be split (the task kernel keeps one CTA group per tile)
+        const bool mega_wave = mega_eligible(c) && c->d_mega && !c->profiling && !c->timeline;
+        if (c->trsm_split && c->d_rslot && c->i8_which == 3 && c->fuse_slices && c->i8_group >= c->nblk && !mega_wave) g.rslot = c->d_rslot;
         PhaseScope ps(c, st, PH_SLICE, cur);
         i8_rowscale_kernel<<<dim3((c->npad + 255) / 256, nmat), 256, 0, st>>>(g, c->npad, nullptr, 0);
         LAUNCH_CHECK();
@@ -870,6 +885,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             gs.quad = g.quad + m0;
             gs.info = g.info + m0;
             gs.refine = g.refine + (size_t)m0 * g.refine_blocks;
+            if (g.rslot) gs.rslot = g.rslot + rslot_off(g.nblk, m0, 0, 0, 0);
             gs.nmat = m1 - m0;
             gs.mat0 = m0;
             if (g.S8) {

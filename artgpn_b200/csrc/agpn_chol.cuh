@@ -65,7 +65,14 @@ struct CholArgs {
                                 // diagonal block (the persistent task kernel, where panel solves of column k may still run
                                 // when diagonal block k + 1 is factorised -- Linv is then kept per column too, linv_blocks = nblk)
     double refine_ratio = 1.0e3;
+    // split panel solves (trsm_kernel with one CTA per 64-column half of a tile): the two CTAs' sums L_ik z_k of the folded
+    // forward solve are parked here and subtracted from rhs by the next reader in a fixed order (bit-reproducible):
+    // [nmat][nblk][2 column parity][2 halves][TB]; nullptr: one CTA per tile updates rhs itself
+    double* rslot = nullptr;
 };
+__host__ __device__ __forceinline__ size_t rslot_off(int nblk, int mat, int ti, int parity, int h) {
+    return ((((size_t)mat * nblk + ti) * 2 + parity) * 2 + h) * 128;
+}
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -413,7 +420,8 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
 // body of the panel solve for tile (ti, k) of matrix `mat`: all 256 threads of the CTA; `smem` = GEMM_SMEM_BYTES of
 // dynamic shared memory, `pipe` = the CTA's operand pipeline (its chunk counter runs on across calls)
 template <bool G = false>
-__device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int flags, int ti, int mat, double* smem, GemmPipe& pipe) {
+__device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int flags, int ti, int mat, double* smem, GemmPipe& pipe,
+                                          int hsel = -1) {
     __shared__ double zs_[G ? 2 : 1][TB];
     __shared__ double qs_[G ? 2 : 1][TB];      // Q / r_i of this row tile (digit planes)
     __shared__ double red_[G ? 2 : 1][2][TB];
@@ -433,6 +441,22 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
     // ill-conditioned diagonal block (flag set by potrf_diag_kernel): X L_kk^T = A_ik by substitution, in place, one
     // thread per row, 16 columns at a time in registers; L_kk sits packed (lower triangle) in the pipeline buffers
     const bool refine = g.refine != nullptr && g.refine[(size_t)mat * g.refine_blocks + (g.refine_blocks > 1 ? k : 0)] != 0;   // CTA-uniform
+    // hsel >= 0: this CTA solves only the 64-column half hsel of the tile (its partner the other one).  The substitution solve
+    // is not split: the h = 1 CTA takes the whole tile, the h = 0 CTA only keeps the hand-over of the forward-solve sums going
+    const bool split = hsel >= 0 && g.rslot != nullptr && rhs != nullptr;
+    if (hsel >= 0 && refine) {
+        if (hsel == 0) {
+            if (split && tid < TB) {
+                if (k > 0) {
+                    const double* pp = g.rslot + rslot_off(g.nblk, mat, ti, (k - 1) & 1, 0);
+                    rhs[(size_t)ti * TB + tid] -= pp[tid] + pp[TB + tid];
+                }
+                g.rslot[rslot_off(g.nblk, mat, ti, k & 1, 0) + tid] = 0.0;
+            }
+            return;
+        }
+        hsel = -1;
+    }
     if (refine) {
         const double* Lkk = A + (size_t)k * TB * ld + (size_t)k * TB;
         for (int idx = tid; idx < TB * TB; idx += 256) {
@@ -471,6 +495,7 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         const int h = 1 - pass;
+        if (hsel >= 0 && h != hsel) continue;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -546,7 +571,20 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
             if ((lane & 3) == 0) red[wn][wm * 32 + mi * 8 + (lane >> 2)] = s;
         }
         grp_sync<G>();
-        if (tid < TB) rhs[(size_t)ti * TB + tid] -= red[0][tid] + red[1][tid];
+        if (tid < TB) {
+            if (split) {
+                // the h = 0 CTA subtracts the previous column's two sums (both complete: the previous launch), then both park theirs;
+                // the h = 1 CTA of an un-split (substitution) tile parks the whole sum
+                const int hh = hsel >= 0 ? hsel : 1;
+                if (hh == 0 && k > 0) {
+                    const double* pp = g.rslot + rslot_off(g.nblk, mat, ti, (k - 1) & 1, 0);
+                    rhs[(size_t)ti * TB + tid] -= pp[tid] + pp[TB + tid];
+                }
+                g.rslot[rslot_off(g.nblk, mat, ti, k & 1, hh) + tid] = red[0][tid] + red[1][tid];
+            } else {
+                rhs[(size_t)ti * TB + tid] -= red[0][tid] + red[1][tid];
+            }
+        }
     }
 }
 
@@ -554,7 +592,9 @@ __global__ void __launch_bounds__(256, 2) trsm_kernel(CholArgs g, int k, int k0,
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) unsigned long long bars[2 * GEMM_STAGES];
     GemmPipe pipe = gemm_pipe_init(bars);
-    trsm_body(g, k, k0, flags, k + 1 + (int)blockIdx.x, (int)blockIdx.y, smem, pipe);
+    // flags bit 3: grid.x = 2 (nblk - k - 1), one CTA per 64-column half of a tile (the heavier right half first)
+    if (flags & 8) trsm_body(g, k, k0, flags, k + 1 + (int)(blockIdx.x >> 1), (int)blockIdx.y, smem, pipe, 1 - (int)(blockIdx.x & 1));
+    else trsm_body(g, k, k0, flags, k + 1 + (int)blockIdx.x, (int)blockIdx.y, smem, pipe);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -683,7 +723,15 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
             }
         }
     }
-    if (rhs != nullptr && tid < TB) zs[tid] = rhs[tid];
+    if (rhs != nullptr && tid < TB) {
+        double r = rhs[tid];
+        if (g.rslot != nullptr && k > 0) {
+            // split panel solves: the last column's two half-tile sums L_k,k-1 z_k-1 are still parked (fixed order)
+            const double* pp = g.rslot + rslot_off(g.nblk, mat, k, (k - 1) & 1, 0);
+            r -= pp[tid] + pp[TB + tid];
+        }
+        zs[tid] = r;
+    }
     grp_sync<G>();
 
     // ---- factor: panels of 16 columns; the diagonal block of panel pb+1 (serial, one warp) is
