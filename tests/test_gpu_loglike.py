@@ -183,9 +183,10 @@ def _cond_goldens():
 
 # The log-likelihood of an ill-conditioned block moves by ~cond(K) * d for a relative change d of the covariance
 # entries, and the reference's own entries carry last-ulp (libm) and argument-rounding noise: two correct
-# implementations agree to ~cond(K) * eps at best.  Bound: max(1e-9, 50 cond eps) -- the 1e-9 of the north_star holds
-# up to cond ~ 1e5 / eps * 1e-9 ~ 1e5..1e6, beyond that parity degrades linearly in cond, for any implementation.
-COND_FACTOR = 50.0
+# implementations agree to ~cond(K) * eps at best.  Bound: max(1e-9, 2 cond eps) (measured: ~0.03 cond eps in every mode,
+# DESIGN.md section 4.4) -- the 1e-9 of the north_star holds up to cond ~ 1e6, beyond that parity degrades linearly in
+# cond, for any implementation.
+COND_FACTOR = 2.0
 
 
 @pytest.mark.parametrize("mode", ["i8", "dmma"])
