@@ -147,6 +147,7 @@ struct agpn_ctx {
     bool group_fixed = false;  // AGPN_GROUP given: no adaptation to the batch size
     int group_eff = 8;         // group used by the current call (set from the TOTAL number of matrices)
     bool no_fast_asm = false;  // AGPN_GENERIC_ASM=1 forces the generic assembly kernel
+    bool old_generic_asm = false;   // AGPN_GENERIC_ASM=2: the per-entry generic kernel (assemble_kernel) instead of assemble_block_kernel
     bool no_small = false;     // AGPN_NO_SMALL=1 disables the fused small-N kernel
     bool exact = false;        // agpn_set_exact: reference operation order in every kernel evaluation
     // sub-batch streams: the matrices of a batch are split over nsub streams so that one sub-batch's
@@ -284,7 +285,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     c->tmean = host_mean(time, N);
     c->t0 = time[0];
     if (const char* e = getenv("AGPN_GROUP")) { c->group = atoi(e) > 0 ? atoi(e) : 8; c->group_fixed = true; }
-    if (const char* e = getenv("AGPN_GENERIC_ASM")) c->no_fast_asm = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_GENERIC_ASM")) { c->no_fast_asm = atoi(e) != 0; c->old_generic_asm = atoi(e) == 2; }
     if (const char* e = getenv("AGPN_NO_SMALL")) c->no_small = atoi(e) != 0;
     if (const char* e = getenv("AGPN_SYRK")) { c->use_tma = strncmp(e, "tma", 3) == 0; c->tma_mc = strcmp(e, "tma_nomc") != 0;
         c->tma_which = strcmp(e, "tma_narrow") == 0 ? 1 : (strcmp(e, "tma_wide") == 0 ? 2 : 3); }
@@ -772,6 +773,15 @@ static int launch_assemble(agpn_ctx* c, AsmArgs& a, int W, cudaStream_t st) {
             case 2: launch_fast<2>(c, a, wse, grid, st); break;
             case 3: launch_fast<3>(c, a, wse, grid, st); break;
             default: launch_fast<4>(c, a, wse, grid, st); break;
+        }
+    } else if (!a.exact && a.nser <= 4 && !c->old_generic_asm) {
+        // generic path, dispatch on the kernel class hoisted out of the entry loop
+        const dim3 grid(tiles, W);
+        switch (a.nser) {
+            case 1: assemble_block_kernel<1><<<grid, 256, 0, st>>>(c->S, a); break;
+            case 2: assemble_block_kernel<2><<<grid, 256, 0, st>>>(c->S, a); break;
+            case 3: assemble_block_kernel<3><<<grid, 256, 0, st>>>(c->S, a); break;
+            default: assemble_block_kernel<4><<<grid, 256, 0, st>>>(c->S, a); break;
         }
     } else {
         assemble_kernel<<<dim3(tiles, W), 256, 0, st>>>(c->S, a);
@@ -1570,48 +1580,91 @@ extern "C" int agpn_predict_cov(agpn_ctx* c, const double* theta, int series, in
     CUDA_TRY(cudaMemcpyAsync(d_th + D, th2.data(), sizeof(double) * D, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_ts, tstar, sizeof(double) * M, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));       // th2 is a local
-    CUDA_TRY(cudaMemsetAsync(d_rhs, 0, sizeof(double) * T, st));
-    CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 4 * c->cap_mats, st));
+    // The Schur update K** - (K* L^-T)(K* L^-T)^T runs on the INT8 tensor path like the likelihood's trailing updates (one group
+    // of the training block columns, then ONE wide update of the trailing block); if an entry of K* L^-T exceeds its row scale
+    // sqrt(K**_ii + s^2) -- a covariance that is not jointly positive semi-definite -- everything is redone on DMMA
+    const int nrt = (int)(T / TB);
+    const bool try_i8 = c->i8_which == 3 && !c->predict_dmma && c->nblk > 2 && c->nblk <= 256;
+    const size_t s8_bytes = try_i8 ? i8_slices_per_matrix(nrt, c->nblk) : 0;
+    if (try_i8) {
+        if (s8_bytes > c->cap_ps8) {
+            cudaFree(c->d_ps8);
+            c->d_ps8 = nullptr;
+            c->cap_ps8 = 0;
+            CUDA_TRY(cudaMalloc(&c->d_ps8, s8_bytes));
+            c->cap_ps8 = s8_bytes;
+        }
+        if (3 * T + 2 > c->cap_pvec) {
+            cudaFree(c->d_pvec);
+            c->d_pvec = nullptr;
+            c->cap_pvec = 0;
+            CUDA_TRY(cudaMalloc(&c->d_pvec, sizeof(double) * (3 * T + 2)));
+            c->cap_pvec = 3 * T + 2;
+        }
+    }
     int* d_kflag = c->d_info + c->cap_mats;
     int* d_rflag = c->d_info + 2 * c->cap_mats;
-    MeanArgs m;
-    m.theta = d_th; m.t = c->d_t; m.n = c->N; m.n_pad = c->npad; m.tmean = c->tmean; m.t0 = c->t0; m.y = c->d_y;
-    m.out = d_rhs; m.series0 = series; m.nser = 1; m.subtract = 1; m.rflag = d_rflag;
-    mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
-    LAUNCH_CHECK();
-    m.t = d_ts; m.n = M; m.n_pad = M; m.tmean = host_mean(tstar, M); m.t0 = tstar[0]; m.y = nullptr; m.out = d_ms;
-    m.subtract = 0; m.rflag = nullptr;
-    mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
-    LAUNCH_CHECK();
-    // augmented matrix [K + sigma^2 + s^2 , . ; K* , K** + s^2] (arttwo.py:367-387), lower block triangle
-    AsmArgs a;
-    a.theta = d_th + D; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
-    a.yerr = c->d_yerr; a.out = c->d_aug; a.mat_stride = (long long)(T * T); a.ld = (int)T; a.series0 = series; a.nser = 1;
-    a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1; a.use_trig = 1; a.vec2 = 1;
-    a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
-    if (launch_assemble(c, a, 1, st)) return 1;
-    a.theta = d_th; a.ta = d_ts; a.tb = c->d_t; a.na = M; a.nb = c->N; a.rows_out = (int)Mpad; a.cols_out = c->npad;
-    a.out = c->d_aug + npad * T; a.lower_only = 0; a.square = (M == c->N) ? 1 : 0; a.add_err = 0; a.add_jit = 0;
-    a.pad_identity = 0; a.use_trig = 0; a.kflag = nullptr;
-    if (launch_assemble(c, a, 1, st)) return 1;
-    a.ta = d_ts; a.tb = d_ts; a.na = M; a.nb = M; a.rows_out = (int)Mpad; a.cols_out = (int)Mpad;
-    a.out = c->d_aug + npad * T + npad; a.lower_only = 1; a.square = 1; a.add_err = 0; a.add_jit = 1; a.pad_identity = 1;
-    if (launch_assemble(c, a, 1, st)) return 1;
-    // eliminate the training block columns only: the trailing block becomes K** + s^2 - K* K^-1 K*^T and
-    // the trailing part of the right-hand side becomes -K* K^-1 r
-    CholArgs g;
-    g.A = c->d_aug; g.mat_stride = (long long)(T * T); g.ld = (int)T; g.nblk = (int)(T / TB); g.nmat = 1;
-    g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad; g.info = c->d_info;
-    g.A0 = c->d_aug; g.mat0 = 0;
-    g.refine = c->d_info + 3 * c->cap_mats; g.refine_ratio = c->refine_ratio;
-    const bool maps_were = c->maps_valid;
-    c->maps_valid = false;                      // the tensor maps describe the batch workspace, not this matrix
-    c->group_eff = c->group_fixed ? c->group : 2;
-    const int rc = run_cholesky(c, g, st, nullptr, c->nblk);
-    c->maps_valid = maps_were;
-    if (rc) return 1;
+    for (int attempt = try_i8 ? 0 : 1; attempt < 2; ++attempt) {
+        CUDA_TRY(cudaMemsetAsync(d_rhs, 0, sizeof(double) * T, st));
+        CUDA_TRY(cudaMemsetAsync(c->d_logdet, 0, sizeof(double), st));
+        CUDA_TRY(cudaMemsetAsync(c->d_quad, 0, sizeof(double), st));
+        CUDA_TRY(cudaMemsetAsync(c->d_info, 0, sizeof(int) * 4 * c->cap_mats, st));
+        MeanArgs m;
+        m.theta = d_th; m.t = c->d_t; m.n = c->N; m.n_pad = c->npad; m.tmean = c->tmean; m.t0 = c->t0; m.y = c->d_y;
+        m.out = d_rhs; m.series0 = series; m.nser = 1; m.subtract = 1; m.rflag = d_rflag;
+        mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
+        LAUNCH_CHECK();
+        m.t = d_ts; m.n = M; m.n_pad = M; m.tmean = host_mean(tstar, M); m.t0 = tstar[0]; m.y = nullptr; m.out = d_ms;
+        m.subtract = 0; m.rflag = nullptr;
+        mean_kernel<<<dim3(1, 1), 256, 0, st>>>(c->S, m);
+        LAUNCH_CHECK();
+        // augmented matrix [K + sigma^2 + s^2 , . ; K* , K** + s^2] (arttwo.py:367-387), lower block triangle
+        AsmArgs a;
+        a.theta = d_th + D; a.ta = c->d_t; a.tb = c->d_t; a.na = c->N; a.nb = c->N; a.rows_out = c->npad; a.cols_out = c->npad;
+        a.yerr = c->d_yerr; a.out = c->d_aug; a.mat_stride = (long long)(T * T); a.ld = (int)T; a.series0 = series; a.nser = 1;
+        a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1; a.use_trig = 1; a.vec2 = 1;
+        a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
+        if (launch_assemble(c, a, 1, st)) return 1;
+        a.theta = d_th; a.ta = d_ts; a.tb = c->d_t; a.na = M; a.nb = c->N; a.rows_out = (int)Mpad; a.cols_out = c->npad;
+        a.out = c->d_aug + npad * T; a.lower_only = 0; a.square = (M == c->N) ? 1 : 0; a.add_err = 0; a.add_jit = 0;
+        a.pad_identity = 0; a.use_trig = 0; a.kflag = nullptr;
+        if (launch_assemble(c, a, 1, st)) return 1;
+        a.ta = d_ts; a.tb = d_ts; a.na = M; a.nb = M; a.rows_out = (int)Mpad; a.cols_out = (int)Mpad;
+        a.out = c->d_aug + npad * T + npad; a.lower_only = 1; a.square = 1; a.add_err = 0; a.add_jit = 1; a.pad_identity = 1;
+        if (launch_assemble(c, a, 1, st)) return 1;
+        // eliminate the training block columns only: the trailing block becomes K** + s^2 - K* K^-1 K*^T and
+        // the trailing part of the right-hand side becomes -K* K^-1 r
+        CholArgs g;
+        g.A = c->d_aug; g.mat_stride = (long long)(T * T); g.ld = (int)T; g.nblk = (int)(T / TB); g.nmat = 1;
+        g.Linv = c->d_Linv; g.linv_blocks = 1; g.rhs = d_rhs; g.logdet = c->d_logdet; g.quad = c->d_quad; g.info = c->d_info;
+        g.A0 = c->d_aug; g.mat0 = 0;
+        g.refine = c->d_info + 3 * c->cap_mats; g.refine_ratio = c->refine_ratio;
+        const bool maps_were = c->maps_valid;
+        c->maps_valid = false;                      // the tensor maps describe the batch workspace, not this matrix
+        int* d_wrap = nullptr;
+        if (attempt == 0) {
+            double* d_rs = c->d_pvec;                              // [2][T] row scales | wrap flag
+            d_wrap = reinterpret_cast<int*>(c->d_pvec + 2 * T);
+            CUDA_TRY(cudaMemsetAsync(d_wrap, 0, sizeof(int), st));
+            g.S8 = c->d_ps8; g.rscale = d_rs; g.sgroup = c->nblk; g.i8flag = d_wrap;
+            i8_rowscale_kernel<<<dim3((unsigned)((T + 255) / 256), 1), 256, 0, st>>>(g, (int)T, nullptr, 0);
+            LAUNCH_CHECK();
+            c->group_eff = c->nblk;
+            if (!c->i8_clusters_fixed) c->i8_clusters = c->i8_clusters_max;
+        } else {
+            c->group_eff = c->group_fixed ? c->group : 2;
+        }
+        const int rc = run_cholesky(c, g, st, nullptr, c->nblk);
+        c->maps_valid = maps_were;
+        if (rc) return 1;
+        c->last_predict_path = attempt == 0 ? 1 : 0;
+        if (attempt == 0) {
+            int wrapped = 0;
+            CUDA_TRY(cudaMemcpyAsync(&wrapped, d_wrap, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (!wrapped && !c->predict_test_wrap) break;
+        }
+    }
     double* d_cov = nullptr;
     CUDA_TRY(cudaMalloc(&d_cov, sizeof(double) * (size_t)M * M));
     extract_cov_kernel<<<1024, 256, 0, st>>>(c->d_aug, (int)T, c->npad, M, d_rhs, d_ms, d_mu, d_cov);

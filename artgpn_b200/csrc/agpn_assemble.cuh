@@ -406,6 +406,261 @@ __global__ void __launch_bounds__(256, 2) assemble_fast_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Generic assembly, blocked by kernel class (round 2).  assemble_kernel above evaluates every entry through one out-of-line
+// `switch` per (entry, node) and per (entry, series, node) with library pow / exp -- 12.7 % of the HBM roof on a
+// Matern52 + RationalQuadratic network.  Here the dispatch on the kernel class is hoisted out of the entry loop: a thread owns
+// 2 adjacent columns x 4 rows (8 entries) at a time, and for each node / weight kernel ONE switch selects a loop over those
+// 8 entries that is specialised at compile time for the class (shape_block<KIND>); exponentials of non-positive arguments
+// use the table-based exp_nonpos, powers exp(alpha log B).  Same output layout, flags and quirks as assemble_kernel
+// (which stays for the exact mode and for more than four series per launch).
+// ---------------------------------------------------------------------------------------------
+#define ASMB_R 4        // rows per thread per block of entries
+
+__device__ __forceinline__ double exp_any(double x, const double* __restrict__ tab) { return x <= 0.0 ? exp_nonpos(x, tab) : exp(x); }
+
+template <int KIND>
+__device__ __forceinline__ void shape_block(const PKern& k, const double (&r)[ASMB_R][2], const double (&t1)[ASMB_R], const double (&t2)[2],
+                                            const bool (&dg)[ASMB_R][2], const double (*sinv)[2], const double* __restrict__ etab,
+                                            double (&out)[ASMB_R][2]) {
+#pragma unroll
+    for (int u = 0; u < ASMB_R; ++u)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double rv = r[u][e], ar = fabs(rv);
+            double v;
+            if (KIND == K_CONSTANT) v = 1.0;
+            else if (KIND == K_WHITENOISE) v = dg[u][e] ? 1.0 : 0.0;
+            else if (KIND == K_SE) v = exp_any(k.a * rv * rv, etab);
+            else if (KIND == K_PERIODIC) {
+                const double sn = sinv ? sinv[u][e] : sin(k.b * ar);
+                v = exp_any(k.a * sn * sn, etab);
+            } else if (KIND == K_QP) {
+                const double sn = sinv ? sinv[u][e] : sin(k.b * ar);
+                v = exp_any(fma(k.a * sn, sn, k.c * rv * rv), etab);
+            } else if (KIND == K_RQ) {
+                const double B = fma(k.a * rv, rv, 1.0);
+                v = (B > 0.0) ? exp_any(-k.b * log(B), etab) : 1.0 / pow(B, k.b);
+            } else if (KIND == K_RQP) {
+                const double sn = sinv ? sinv[u][e] : sin(k.b * ar);
+                v = kern_shape_with_sin(k, rv, sn);
+            } else if (KIND == K_COSINE) v = cos(k.a * ar);
+            else if (KIND == K_EXP) v = exp_any(k.a * ar, etab);
+            else if (KIND == K_M32) {
+                const double x = k.a * ar;
+                v = (1.0 + x) * exp_any(-x, etab);
+            } else if (KIND == K_M52) v = (1.0 + (k.a * ar + 5.0 * rv * rv) * k.b) * exp_any(k.c * ar, etab);
+            else if (KIND == K_LINEAR) v = (t1[u] - k.a) * (t2[e] - k.a);
+            else if (KIND == K_GAMMAEXP) v = exp(-pow(ar * k.a, k.b));
+            else v = pow(k.a * t1[u] * t2[e] + k.b, k.c);          // K_POLY
+            out[u][e] = v;
+        }
+}
+
+__device__ __forceinline__ void shape_block_dispatch(const PKern& k, const double (&r)[ASMB_R][2], const double (&t1)[ASMB_R],
+                                                     const double (&t2)[2], const bool (&dg)[ASMB_R][2], const double (*sinv)[2],
+                                                     const double* __restrict__ etab, double (&out)[ASMB_R][2]) {
+    switch (k.kind) {
+        case K_CONSTANT: shape_block<K_CONSTANT>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_WHITENOISE: shape_block<K_WHITENOISE>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_SE: shape_block<K_SE>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_PERIODIC: shape_block<K_PERIODIC>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_QP: shape_block<K_QP>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_RQ: shape_block<K_RQ>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_RQP: shape_block<K_RQP>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_COSINE: shape_block<K_COSINE>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_EXP: shape_block<K_EXP>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_M32: shape_block<K_M32>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_M52: shape_block<K_M52>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_LINEAR: shape_block<K_LINEAR>(k, r, t1, t2, dg, sinv, etab, out); break;
+        case K_GAMMAEXP: shape_block<K_GAMMAEXP>(k, r, t1, t2, dg, sinv, etab, out); break;
+        default: shape_block<K_POLY>(k, r, t1, t2, dg, sinv, etab, out); break;
+    }
+}
+
+#ifndef ASMB_MINB
+#define ASMB_MINB 2             // two CTAs per SM (128 registers, some spills): 1.20 vs 1.36 ms on the Matern52 + RationalQuadratic probe
+#endif
+template <int NSER>
+__global__ void __launch_bounds__(256, ASMB_MINB) assemble_block_kernel(const __grid_constant__ Structure S, const AsmArgs g) {
+    __shared__ PKern s_node[AGPN_MAXQ];
+    __shared__ PKern s_weight[NSER * AGPN_MAXQ];
+    __shared__ int s_slot[AGPN_MAXQ];
+    __shared__ double s_ta[ASM_TILE], s_tb[ASM_TILE];
+    __shared__ double s_diag[NSER][ASM_TILE];
+    __shared__ double s_trig[ASM_NTRIG][4][ASM_TILE];   // [slot][sin row, cos row, sin col, cos col]
+    __shared__ __align__(128) double s_etab[16];
+
+    const int tid = threadIdx.x;
+    const int w = blockIdx.y;
+    const int q = S.q;
+    if (tid >= 240) s_etab[tid - 240] = c_exp2_16[tid - 240];
+    int bi, bj;
+    if (g.lower_only) {
+        const int t = blockIdx.x;
+        bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        while (bi * (bi + 1) / 2 > t) --bi;
+        bj = t - bi * (bi + 1) / 2;
+    } else {
+        const int tcols = (g.cols_out + ASM_TILE - 1) / ASM_TILE;
+        bi = blockIdx.x / tcols;
+        bj = blockIdx.x % tcols;
+    }
+    const int i0 = bi * ASM_TILE, j0 = bj * ASM_TILE;
+    const double* th = g.theta + (size_t)w * S.D;
+
+    if (tid < q) {
+        s_node[tid] = prep_kernel(0, S.node_kind[tid], th + S.node_off[tid]);
+    } else if (tid >= 32 && tid < 32 + NSER * q) {
+        const int u = tid - 32;
+        const int sidx = u / q, j = u % q;
+        const int widx = j + q * (g.series0 + sidx);
+        s_weight[u] = prep_kernel(1, S.weight_kind[widx], th + S.weight_off[widx]);
+    }
+    if (tid == 64) {
+        int slot = 0;
+        for (int j = 0; j < AGPN_MAXQ; ++j) {
+            int v = -1;
+            if (j < q && g.use_trig && kernel_has_sin(S.node_kind[j]) && slot < ASM_NTRIG) v = slot++;
+            s_slot[j] = v;
+        }
+    }
+    if (tid < ASM_TILE) {
+        const int gi = i0 + tid;
+        s_ta[tid] = g.ta[gi < g.na ? gi : g.na - 1];
+    } else {
+        const int gj = j0 + tid - ASM_TILE;
+        s_tb[tid - ASM_TILE] = g.tb[gj < g.nb ? gj : g.nb - 1];
+    }
+    if (bi == bj && (g.add_err || g.add_jit)) {
+        for (int u = tid; u < NSER * ASM_TILE; u += 256) {
+            const int sidx = u / ASM_TILE, r = u % ASM_TILE;
+            const int gi = i0 + r;
+            double v = 0.0;
+            if (gi < g.na) {
+                if (g.add_err) {
+                    const double e = g.yerr[(size_t)(g.series0 + sidx) * g.na + gi];
+                    v += e * e;
+                }
+                if (g.add_jit) {
+                    const double jt = th[S.jit_off + g.series0 + sidx];
+                    v += jt * jt;
+                }
+            }
+            s_diag[sidx][r] = v;
+        }
+    }
+    __syncthreads();
+    if (g.use_trig) {
+        for (int j = 0; j < q; ++j) {
+            const int slot = s_slot[j];
+            if (slot < 0) continue;
+            const double per = s_node[j].per;
+            double sv, cv;
+            if (tid < ASM_TILE) {
+                phase_sincos(s_ta[tid] - g.torigin, per, &sv, &cv);
+                s_trig[slot][0][tid] = sv;
+                s_trig[slot][1][tid] = cv;
+            } else {
+                phase_sincos(s_tb[tid - ASM_TILE] - g.torigin, per, &sv, &cv);
+                s_trig[slot][2][tid - ASM_TILE] = sv;
+                s_trig[slot][3][tid - ASM_TILE] = cv;
+            }
+        }
+        __syncthreads();
+    }
+
+    const int tx = tid & 63, ty = tid >> 6;
+    const int c0 = 2 * tx;
+    const double t2[2] = {s_tb[c0], s_tb[c0 + 1]};
+    const int gj0 = j0 + c0;
+    unsigned bad = 0;
+#pragma unroll 1
+    for (int rb = 0; rb < ASM_TILE / 4; rb += ASMB_R) {
+        // rows ty + 4 (rb + u), u < ASMB_R
+        double r[ASMB_R][2], t1[ASMB_R], v[NSER][ASMB_R][2];
+        bool dg[ASMB_R][2];
+#pragma unroll
+        for (int u = 0; u < ASMB_R; ++u) {
+            const int row = ty + 4 * (rb + u);
+            const int gi = i0 + row;
+            t1[u] = s_ta[row];
+            r[u][0] = t1[u] - t2[0];
+            r[u][1] = t1[u] - t2[1];
+            dg[u][0] = g.square && (gi + g.row_off == gj0);
+            dg[u][1] = g.square && (gi + g.row_off == gj0 + 1);
+#pragma unroll
+            for (int sidx = 0; sidx < NSER; ++sidx) v[sidx][u][0] = v[sidx][u][1] = 0.0;
+        }
+        for (int j = 0; j < q; ++j) {
+            const PKern& kn = s_node[j];
+            const int slot = s_slot[j];
+            double sinv[ASMB_R][2], F[ASMB_R][2];
+            if (slot >= 0) {
+#pragma unroll
+                for (int u = 0; u < ASMB_R; ++u) {
+                    const int row = ty + 4 * (rb + u);
+                    const double sr = s_trig[slot][0][row], cr = s_trig[slot][1][row];
+                    sinv[u][0] = sr * s_trig[slot][3][c0] - cr * s_trig[slot][2][c0];
+                    sinv[u][1] = sr * s_trig[slot][3][c0 + 1] - cr * s_trig[slot][2][c0 + 1];
+                }
+            }
+            shape_block_dispatch(kn, r, t1, t2, dg, slot >= 0 ? sinv : nullptr, s_etab, F);
+#pragma unroll
+            for (int sidx = 0; sidx < NSER; ++sidx) {
+                const PKern& kw = s_weight[sidx * q + j];
+                const double amp = kw.amp * kn.amp;
+                if (kw.kind == K_CONSTANT) {
+#pragma unroll
+                    for (int u = 0; u < ASMB_R; ++u) {
+                        v[sidx][u][0] = fma(amp, F[u][0], v[sidx][u][0]);
+                        v[sidx][u][1] = fma(amp, F[u][1], v[sidx][u][1]);
+                    }
+                } else {
+                    double Wt[ASMB_R][2];
+                    shape_block_dispatch(kw, r, t1, t2, dg, nullptr, s_etab, Wt);
+#pragma unroll
+                    for (int u = 0; u < ASMB_R; ++u) {
+                        v[sidx][u][0] = fma(amp * Wt[u][0], F[u][0], v[sidx][u][0]);
+                        v[sidx][u][1] = fma(amp * Wt[u][1], F[u][1], v[sidx][u][1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ASMB_R; ++u) {
+            const int row = ty + 4 * (rb + u);
+            const int gi = i0 + row;
+            if (gi >= g.rows_out) continue;
+#pragma unroll
+            for (int sidx = 0; sidx < NSER; ++sidx) {
+                double v0 = v[sidx][u][0], v1 = v[sidx][u][1];
+                if (bi == bj && (g.add_err || g.add_jit)) {
+                    if (gi == gj0) v0 += s_diag[sidx][row];
+                    if (gi == gj0 + 1) v1 += s_diag[sidx][row];
+                }
+                const bool in0 = (gi < g.na) && (gj0 < g.nb), in1 = (gi < g.na) && (gj0 + 1 < g.nb);
+                if (!in0) v0 = (g.pad_identity && gi == gj0) ? 1.0 : 0.0;
+                if (!in1) v1 = (g.pad_identity && gi == gj0 + 1) ? 1.0 : 0.0;
+                if (!isfinite(v0) || !isfinite(v1)) bad |= 1u << sidx;
+                double* dst = g.out + (size_t)((size_t)w * NSER + sidx) * g.mat_stride + (size_t)gi * g.ld + gj0;
+                if (g.vec2 && gj0 + 1 < g.cols_out) {
+                    *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                } else {
+                    if (gj0 < g.cols_out) dst[0] = v0;
+                    if (gj0 + 1 < g.cols_out) dst[1] = v1;
+                }
+            }
+        }
+    }
+    if (bad && g.kflag != nullptr) {
+#pragma unroll
+        for (int sidx = 0; sidx < NSER; ++sidx)
+            if (bad & (1u << sidx)) g.kflag[(size_t)w * NSER + sidx] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct MeanArgs {
     const double* theta;   // [W][D]
     const double* t;       // [n]

@@ -298,3 +298,33 @@ def test_posterior_samples_have_the_predictive_moments():
     C = np.cov(S.T)
     assert np.max(np.abs(C - cov)) <= 6.0 * np.max(np.diag(cov)) / np.sqrt(S.shape[0])
     net.close()
+
+
+def test_predictive_covariance_on_the_int8_path_and_its_fallback(monkeypatch):
+    """agpn_predict_cov: the Schur update of the trailing block runs on the INT8 tensor path (predict_path 1); forcing the
+    fall-back (AGPN_I8_TEST_WRAP=1) or the FP64 instruction (AGPN_PREDICT=dmma) gives the same covariance to round-off,
+    and all of them match the reference form of the oracle."""
+    from artgpn_b200 import synth, node, weight, mean
+    t, y, sig = synth.make_data(700, 2, seed=6)
+    theta = synth.make_walkers(1, p=2, q=2, seed=3)[0]
+    grid = np.linspace(t.min() - 2, t.max() + 2, 300)
+    m = _Spec()
+    oo = synth.objects_from_row(m, m, m, theta, 2, 2)
+    emu, esd, ecov = oracle.prediction_reference_form(t, y, sig, 2, *oo, grid, 2, return_cov=True)
+    got = {}
+    for name, env in (("i8", {}), ("fallback", {"AGPN_I8_TEST_WRAP": "1"}), ("dmma", {"AGPN_PREDICT": "dmma"})):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        net, _ = _net(700, 2, 2, seed=6)
+        o = synth.objects_from_row(node, weight, mean, theta, 2, 2)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mu, sd, cov = net.prediction_cov(o[0], o[1], o[2], o[3], grid, 2)
+        assert net.predict_path() == (1 if name == "i8" else 0), name
+        got[name] = (mu, cov)
+        net.close()
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        assert np.max(np.abs(mu - emu)) <= 1e-9 * np.max(np.abs(emu)), name
+        assert np.max(np.abs(cov - ecov)) <= 1e-9 * np.max(np.abs(np.diag(ecov))), name
+    assert np.max(np.abs(got["i8"][1] - got["dmma"][1])) <= 1e-11 * np.max(np.abs(np.diag(ecov)))
+    assert np.array_equal(got["fallback"][1], got["dmma"][1])
