@@ -534,6 +534,7 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
             grp_sync<G>();                                       // slower warps may still read the last operand stages
             unsigned char* stg = reinterpret_cast<unsigned char*>(smem);      // [wn = 32-column chunk][slice][4096]
             int wrapped = 0;
+            const bool check_wrap = g.i8flag != nullptr;        // only the prediction paths can exceed a row scale
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
                 const double f = qs[wm * 32 + mi * 8 + (lane >> 2)];
@@ -541,7 +542,7 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
                 for (int ni = 0; ni < 4; ++ni) {
                     unsigned piece[I8_NSL];
                     const double x0 = acc[mi][ni][0] * f, x1 = acc[mi][ni][1] * f;
-                    if (fmax(fabs(x0), fabs(x1)) > I8_QMAXF) wrapped = 1;
+                    if (check_wrap && fmax(fabs(x0), fabs(x1)) > I8_QMAXF) wrapped = 1;
                     i8_digits2(x0, x1, piece);
                     unsigned char* dst = stg + wn * I8_TILE_BYTES + (wm * 4 + mi) * 256 + (ni >> 1) * 128 + (lane >> 2) * 16 +
                                          (ni & 1) * 8 + 2 * (lane & 3);
@@ -804,11 +805,16 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
     }
 
     // ---- write L back (lower triangle incl. diagonal) -----------------------------------------------
-    for (int i = tid >> 7; i < TB; i += 2) {
-        const int c = tid & 127;
-        if (c <= i) Akk[(size_t)i * ld + c] = S[i * PD_LD + c];
+    for (int i = tid >> 6; i < TB; i += 4) {               // 16-byte stores; the element right of the diagonal is a zero
+        const int c = 2 * (tid & 63);
+        if (c <= i) {
+            double2 v = *reinterpret_cast<const double2*>(S + i * PD_LD + c);
+            if (c + 1 > i) v.y = 0.0;
+            *reinterpret_cast<double2*>(Akk + (size_t)i * ld + c) = v;
+        }
     }
 
+    double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
     // ---- inverse, step 1: the eight 16 x 16 diagonal inverses, warp w -> block w, lane c -> column c --
     {
         const int c0 = warp * 16;
@@ -893,7 +899,9 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
 #pragma unroll
                     for (int ni = 0; ni < 2; ++ni) dmma884(y[mi][ni][0], y[mi][ni][1], a[mi], b[ni]);
             }
-            // X_ij[r][c] -> transposed into the upper triangle: S[16 j + c][16 i + r]
+            // X_ij[r][c] -> transposed into the upper triangle: S[16 j + c][16 i + r] (operand of the later block rows),
+            // and straight to global memory from the accumulator layout (16-byte stores, 64 contiguous bytes per row):
+            // the write-out loop below then has no bank-conflicted transposed reads left
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -901,20 +909,18 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
                     const int rr = 8 * mi + (lane >> 2), cc = 8 * ni + 2 * (lane & 3);
                     S[(16 * j + cc) * PD_LD + 16 * i + rr] = y[mi][ni][0];
                     S[(16 * j + cc + 1) * PD_LD + 16 * i + rr] = y[mi][ni][1];
+                    *reinterpret_cast<double2*>(Linv + (16 * i + rr) * TB + 16 * j + cc) = make_double2(y[mi][ni][0], y[mi][ni][1]);
                 }
             __syncwarp();
         }
     }
     grp_sync<G>();
 
-    // ---- write the inverse (full tile, zeros above the diagonal) -------------------------------------
-    double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
+    // ---- rest of the inverse: the 16 x 16 diagonal blocks and the zeros above them (the blocks below were stored by step 2) ----
     for (int R = tid >> 7; R < TB; R += 2) {
         const int C = tid & 127;
-        double v = 0.0;
-        if ((C >> 4) == (R >> 4)) v = Dv[(R >> 4) * 16 * PD_DV_LD + (R & 15) * PD_DV_LD + (C & 15)];
-        else if (C < R) v = S[C * PD_LD + R];
-        Linv[R * TB + C] = v;
+        if ((C >> 4) == (R >> 4)) Linv[R * TB + C] = Dv[(R >> 4) * 16 * PD_DV_LD + (R & 15) * PD_DV_LD + (C & 15)];
+        else if (C > R) Linv[R * TB + C] = 0.0;
     }
 
     // ---- z_k = Linv r_k ; |z_k|^2 ; sum log L_jj ------------------------------------------------------
