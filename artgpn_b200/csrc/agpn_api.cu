@@ -1161,6 +1161,15 @@ extern "C" int agpn_loglike_batch_sharded(agpn_ctx* c, int W, const double* thet
         CUDA_TRY(cudaMalloc(&c->d_gstatus, sizeof(int) * need));
         c->cap_gather = need;
     }
+    // steady state (even shards, workspace in place, device output, no status): the wave's own result buffer is the send
+    // buffer and the caller's `out` the receive buffer -- no staging copies around the collective
+    if (W % c->nranks == 0 && out_on_device && !status && (size_t)(hi - lo) * c->p <= c->cap_mats && (size_t)(hi - lo) <= c->cap_w &&
+        (size_t)(hi - lo) * c->p <= 65535) {
+        const int rc = agpn_loglike_batch(c, hi - lo, theta + (size_t)lo * c->S.D, theta_on_device, c->d_out, 1, nullptr, stream);
+        if (rc) return rc;
+        NCCL_TRY(n->AllGather(c->d_out, out, (size_t)slot, ncclDouble, c->comm, st));
+        return 0;
+    }
     double* mine = c->d_gather + (size_t)c->rank * slot;          // the likelihood kernels write straight into the send slot
     int* mine_s = c->d_gstatus + (size_t)c->rank * slot;
     if (hi > lo) {
