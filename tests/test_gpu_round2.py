@@ -328,3 +328,15 @@ def test_predictive_covariance_on_the_int8_path_and_its_fallback(monkeypatch):
         assert np.max(np.abs(cov - ecov)) <= 1e-9 * np.max(np.abs(np.diag(ecov))), name
     assert np.max(np.abs(got["i8"][1] - got["dmma"][1])) <= 1e-11 * np.max(np.abs(np.diag(ecov)))
     assert np.array_equal(got["fallback"][1], got["dmma"][1])
+
+
+def test_sample_from_a_multi_block_covariance():
+    """n = 300: three block columns, i.e. the blocked factorisation (panel solves + trailing updates) produces the factor."""
+    from artgpn_b200 import node
+    net, (t, _, _) = _net(300, 1, 1, seed=8)
+    K = net._kernel_matrix(node.Matern52(9.0), t) * 2.5 + 0.02 * np.identity(t.size)
+    z = np.random.default_rng(9).standard_normal((2, t.size))
+    got = net.sample(K, t, size=2, random_state=np.random.default_rng(9))
+    exp = z @ np.linalg.cholesky(K).T
+    assert np.max(np.abs(got - exp)) <= 1e-10 * np.max(np.abs(exp))
+    net.close()
