@@ -153,6 +153,7 @@ struct agpn_ctx {
     // sub-batch streams: the matrices of a batch are split over nsub streams so that one sub-batch's
     // small serial kernels (diagonal block, panel solve) overlap another's wide tensor update
     int nsub = 6;              // AGPN_STREAMS
+    bool nsub_fixed = false;   // AGPN_STREAMS given: no adaptation to the batch size
     cudaStream_t sub[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr;
     // CUDA-graph replay of one wave (memsets, residual, assembly, all Cholesky launches on all sub-streams,
@@ -333,7 +334,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
         cudaEventCreateWithFlags(&c->ev_gin, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_gout, cudaEventDisableTiming) != cudaSuccess)
         c->use_graph = false;
-    if (const char* e = getenv("AGPN_STREAMS")) c->nsub = atoi(e);
+    if (const char* e = getenv("AGPN_STREAMS")) { c->nsub = atoi(e); c->nsub_fixed = true; }
     if (c->nsub < 1) c->nsub = 1;
     if (c->nsub > 8) c->nsub = 8;
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) c->nsub = 1;
@@ -873,7 +874,12 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         i8_rowscale_kernel<<<dim3((c->npad + 255) / 256, nmat), 256, 0, st>>>(g, c->npad, nullptr, 0);
         LAUNCH_CHECK();
     }
-    const int nsub = (c->profiling || c->nsub < 2 || nmat < 2 * c->nsub) ? 1 : c->nsub;
+    // sub-batch streams: six for small batches (latency-bound chains need neighbours to fill the GPU), fewer for large ones,
+    // where every launch fills the GPU by itself and fewer, larger launches pay fewer tails (measured, 3 x 2048: 128 walkers
+    // 20.60 / 20.66 / 20.80 ms with 3 / 4 / 6 streams, 64 walkers 10.56 vs 10.66 with 4 vs 6, 16 walkers 3.32 vs 3.20)
+    int nsub_pref = c->nsub;
+    if (!c->nsub_fixed) nsub_pref = nmat >= 288 ? 3 : (nmat >= 144 ? 4 : c->nsub);
+    const int nsub = (c->profiling || nsub_pref < 2 || nmat < 2 * nsub_pref) ? 1 : nsub_pref;
     if (mega_eligible(c) && g.S8 && c->d_mega && !c->profiling && !c->timeline) {
         // the whole factorisation as ONE persistent launch of tile tasks (agpn_mega.cuh)
         g.refine = c->d_mega + (size_t)nmat * (1 + 2 * (size_t)c->nblk); g.refine_blocks = c->nblk;
