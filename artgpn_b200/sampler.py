@@ -121,11 +121,23 @@ def run_mcmc(prior_func, logpost_func, iterations=1000, sampler="emcee", threads
     prior_func() returns one starting point; 2 * ndim walkers; the first half of `iterations` is
     burn-in; returns the same array layout as the reference's emcee branch: rows = post-burn-in
     samples, columns = parameters followed by the log-probability.  `threads` is ignored (the batch
-    replaces the process pool); sampler must be 'emcee' (the stretch-move algorithm); dynesty's
-    nested sampling is not reproduced.
+    replaces the process pool).  sampler = 'dynesty' follows the reference's second branch (utils.py:155-161:
+    DynamicNestedSampler, nlive 2500, 'rwalk') when the dynesty package is importable -- prior_func is then the prior
+    transform of the unit cube and logpost_func is called with one point at a time ([1, ndim] batches), without the
+    reference's process pool (a CUDA context must not be forked); without dynesty it raises ImportError.
     """
+    if sampler == "dynesty":
+        try:
+            import dynesty
+        except ImportError as e:
+            raise ImportError("run_mcmc(sampler='dynesty') needs the dynesty package (not bundled)") from e
+        ndim = np.asarray(prior_func(0)).size
+        one = lambda th: float(np.asarray(logpost_func(np.asarray(th, dtype=np.float64)[None, :]))[0])      # noqa: E731
+        dsampler = dynesty.DynamicNestedSampler(one, prior_func, ndim=ndim, nlive=2500, sample="rwalk")
+        dsampler.run_nested(nlive_init=2500, maxiter=iterations)
+        return dsampler.results
     if sampler != "emcee":
-        raise NotImplementedError("only the emcee-style ensemble sampler is provided")
+        raise ValueError("sampler must be 'emcee' or 'dynesty'")
     ndim = np.asarray(prior_func()).size
     burns, runs = int(iterations / 2), int(iterations / 2)
     nwalkers = 2 * ndim

@@ -59,3 +59,17 @@ def test_batched_posterior_matches_reference_log_transform_shape():
     rng = np.random.default_rng(3)
     res = run_mcmc(lambda: base[:3] * (1 + 0.01 * rng.normal(size=3)), post3, iterations=20)
     assert res.shape == (6 * 10, 4) and np.all(np.isfinite(res))
+
+
+def test_run_mcmc_dynesty_branch_needs_the_package():
+    """The reference's second branch (utils.py:155-161) is followed when dynesty is importable; it is not part of this image."""
+    from artgpn_b200 import sampler
+    try:
+        import dynesty  # noqa: F401
+        pytest.skip("dynesty is installed: the branch would run a full nested-sampling job")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError):
+        sampler.run_mcmc(lambda u=0: np.zeros(2), lambda th: np.zeros(len(th)), iterations=4, sampler="dynesty")
+    with pytest.raises(ValueError):
+        sampler.run_mcmc(lambda: np.zeros(2), lambda th: np.zeros(len(th)), iterations=4, sampler="other")
