@@ -170,6 +170,10 @@ struct agpn_ctx {
     bool lookahead_forced = false;     // AGPN_LOOKAHEAD=2: for every batch size (default: few matrices only)
     cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_la[8][2] = {};
+    // zero-chunk masks of the digit planes (CholArgs::nzmask): the update skips K steps that would add exact zeros (AGPN_I8_SKIP=0: dense)
+    bool i8_skip = true;
+    unsigned long long* d_nzmask = nullptr;     // [cap_mats][nblk][nzwords]
+    int nzwords = 0;
     // panel solves with one CTA per 64-column half of a tile (AGPN_TRSM_SPLIT=0: one CTA per tile)
     bool trsm_split = true;
     double* d_rslot = nullptr;     // [cap_mats][nblk][2][2][128] parked forward-solve sums of the split panel solves
@@ -296,6 +300,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_I8_BALANCE")) c->i8_balance = atoi(e) != 0;
     if (const char* e = getenv("AGPN_MEGA")) c->use_mega = atoi(e) != 0;
     if (const char* e = getenv("AGPN_TRSM_SPLIT")) c->trsm_split = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_I8_SKIP")) c->i8_skip = atoi(e) != 0;
     if (const char* e = getenv("AGPN_MEGA_PROF")) if (atoi(e) != 0) {
         if (cudaMalloc(&c->d_megaprof, sizeof(unsigned long long) * 16 * 2 * c->i8_clusters_max) != cudaSuccess) { cudaGetLastError(); c->d_megaprof = nullptr; }
     }
@@ -381,7 +386,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_S8); cudaFree(c->d_rscale);
     cudaFree(c->d_paug); cudaFree(c->d_ps8); cudaFree(c->d_pvec);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
-    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot);
+    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot); cudaFree(c->d_nzmask);
     agpn_comm_release(c);
     delete c;
     return 0;
@@ -593,6 +598,13 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_logdet, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 4 * nmat));
+        cudaFree(c->d_nzmask);
+        c->d_nzmask = nullptr;
+        if (c->i8_skip && c->fuse_slices && c->i8_which && c->nblk > 2) {
+            const int sg = c->i8_group < 2 ? 2 : c->i8_group;
+            c->nzwords = (4 * sg + 63) / 64;
+            CUDA_TRY(cudaMalloc(&c->d_nzmask, sizeof(unsigned long long) * nmat * c->nblk * c->nzwords));
+        }
         cudaFree(c->d_rslot);
         c->d_rslot = nullptr;
         if (c->trsm_split && c->i8_which == 3 && c->nblk > 2)
@@ -870,6 +882,11 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         // so every launch can be split (the task kernel keeps one CTA group per tile)
         const bool mega_wave = mega_eligible(c) && c->d_mega && !c->profiling && !c->timeline;
         if (c->trsm_split && c->d_rslot && c->i8_which == 3 && c->fuse_slices && c->i8_group >= c->nblk && !mega_wave) g.rslot = c->d_rslot;
+        if (c->d_nzmask && c->i8_group >= c->nblk) {
+            // masks are rebuilt by every wave's panel solves (one group of all block columns: kc32 = 4 k + chunk)
+            g.nzmask = c->d_nzmask; g.nzwords = c->nzwords;
+            CUDA_TRY(cudaMemsetAsync(c->d_nzmask, 0, sizeof(unsigned long long) * (size_t)nmat * c->nblk * c->nzwords, st));
+        }
         PhaseScope ps(c, st, PH_SLICE, cur);
         i8_rowscale_kernel<<<dim3((c->npad + 255) / 256, nmat), 256, 0, st>>>(g, c->npad, nullptr, 0);
         LAUNCH_CHECK();
@@ -902,6 +919,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             gs.info = g.info + m0;
             gs.refine = g.refine + (size_t)m0 * g.refine_blocks;
             if (g.rslot) gs.rslot = g.rslot + rslot_off(g.nblk, m0, 0, 0, 0);
+            if (g.nzmask) gs.nzmask = g.nzmask + (size_t)m0 * g.nblk * g.nzwords;
             gs.nmat = m1 - m0;
             gs.mat0 = m0;
             if (g.S8) {

@@ -69,6 +69,13 @@ struct CholArgs {
     // forward solve are parked here and subtracted from rhs by the next reader in a fixed order (bit-reproducible):
     // [nmat][nblk][2 column parity][2 halves][TB]; nullptr: one CTA per tile updates rhs itself
     double* rslot = nullptr;
+    // which 32-column chunks of the digit planes hold a non-zero digit at all: bit kc32 of nzmask[mat][row tile][word].
+    // The factor of a covariance whose correlation length is short against the time span is numerically banded -- entries
+    // below 2^-57 of their row scale have ALL digits zero -- and a K step in which either operand chunk is all-zero adds
+    // exact integer zeros: the persistent update skips it (loads, MMAs, and whole tiles without any active step).  Results
+    // are bit-identical to the dense schedule.  nullptr: dense.
+    unsigned long long* nzmask = nullptr;
+    int nzwords = 0;
 };
 __host__ __device__ __forceinline__ size_t rslot_off(int nblk, int mat, int ti, int parity, int h) {
     return ((((size_t)mat * nblk + ti) * 2 + parity) * 2 + h) * 128;
@@ -425,9 +432,11 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
     __shared__ double zs_[G ? 2 : 1][TB];
     __shared__ double qs_[G ? 2 : 1][TB];      // Q / r_i of this row tile (digit planes)
     __shared__ double red_[G ? 2 : 1][2][TB];
+    __shared__ int s_nz_[G ? 2 : 1][2];
     double* zs = zs_[grp_id<G>()];
     double* qs = qs_[grp_id<G>()];
     double (*red)[TB] = red_[grp_id<G>()];
+    int* s_nz = s_nz_[grp_id<G>()];
     double* A = g.A + (size_t)mat * g.mat_stride;
     const int ld = g.ld;
     double* Aik = A + (size_t)ti * TB * ld + (size_t)k * TB;
@@ -531,9 +540,11 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
                 }
             }
         if (flags & 1) {
+            if (tid < 2) s_nz[tid] = 0;
             grp_sync<G>();                                       // slower warps may still read the last operand stages
             unsigned char* stg = reinterpret_cast<unsigned char*>(smem);      // [wn = 32-column chunk][slice][4096]
             int wrapped = 0;
+            unsigned nzbits = 0;
             const bool check_wrap = g.i8flag != nullptr;        // only the prediction paths can exceed a row scale
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
@@ -547,11 +558,19 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
                     unsigned char* dst = stg + wn * I8_TILE_BYTES + (wm * 4 + mi) * 256 + (ni >> 1) * 128 + (lane >> 2) * 16 +
                                          (ni & 1) * 8 + 2 * (lane & 3);
 #pragma unroll
-                    for (int sl = 0; sl < I8_NSL; ++sl) *reinterpret_cast<unsigned short*>(dst + sl * (TB * 32)) = (unsigned short)piece[sl];
+                    for (int sl = 0; sl < I8_NSL; ++sl) {
+                        *reinterpret_cast<unsigned short*>(dst + sl * (TB * 32)) = (unsigned short)piece[sl];
+                        nzbits |= piece[sl];
+                    }
                 }
             }
             if (wrapped && g.i8flag != nullptr) atomicOr(g.i8flag + mat, 1);
+            if (nzbits) s_nz[wn] = 1;                            // this 32-column chunk holds a non-zero digit
             grp_sync<G>();
+            if (g.nzmask != nullptr && tid < 2 && s_nz[tid]) {
+                const int kc32 = 4 * (k - k0) + 2 * h + tid;
+                atomicOr(g.nzmask + ((size_t)mat * g.nblk + ti) * g.nzwords + (kc32 >> 6), 1ull << (kc32 & 63));
+            }
             signed char* S = g.S8 + (size_t)mat * i8_slices_per_matrix(g.nblk, g.sgroup);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {

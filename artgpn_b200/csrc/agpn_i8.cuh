@@ -418,6 +418,24 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// K steps (32-column chunks ks < nks) of tile (ti, tj) in which BOTH operands hold a non-zero digit, 64 per word
+// (CholArgs::nzmask; without masks every step is active)
+__device__ __forceinline__ unsigned long long i8_active_word(const CholArgs& g, int mat, int ti, int tj, int word, int nks) {
+    const int left = nks - word * 64;
+    if (left <= 0) return 0ull;
+    unsigned long long a = ~0ull;
+    if (g.nzmask != nullptr)
+        a = g.nzmask[((size_t)mat * g.nblk + ti) * g.nzwords + word] & g.nzmask[((size_t)mat * g.nblk + tj) * g.nzwords + word];
+    if (left < 64) a &= (1ull << left) - 1ull;
+    return a;
+}
+__device__ __forceinline__ bool i8_any_active(const CholArgs& g, int mat, int ti, int tj, int nks) {
+    if (g.nzmask == nullptr) return nks > 0;
+    for (int wd = 0; wd * 64 < nks; ++wd)
+        if (i8_active_word(g, mat, ti, tj, wd, nks)) return true;
+    return false;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_PTHREADS, 1)
 syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles, int total, int bi0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -486,17 +504,23 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
                 bool diag;
                 decode(w, mat, ti, tj, diag);
                 const signed char* S = g.S8 + (size_t)mat * i8_slices_per_matrix(g.nblk, g.sgroup);
-                for (int ks = 0; ks < nks; ++ks, ++it) {
-                    const unsigned s = it % I8_STAGES, u = it / I8_STAGES;
-                    if (u > 0) mbar_wait(empty + 8 * s, (u - 1) & 1);
-                    mbar_expect_tx(full + 8 * s, I8_STAGE_BYTES);
-                    const unsigned dst = sbase + s * I8_STAGE_BYTES;
-                    bulk_g2s_mc(dst + rank * (4 * I8_A_BYTES), S + i8_tile_off(ks, ti, g.nblk) + rank * (4 * I8_A_BYTES), 4 * I8_A_BYTES,
-                                full + 8 * s, (unsigned short)3);
-                    const signed char* bsrc = S + i8_tile_off(ks, tj, g.nblk) + h * I8_B_BYTES;
+                for (int wd = 0; wd * 64 < nks; ++wd) {
+                    unsigned long long act = i8_active_word(g, mat, ti, tj, wd, nks);     // K steps with non-zero digits on both sides
+                    while (act) {
+                        const int ks = wd * 64 + __ffsll((long long)act) - 1;
+                        act &= act - 1ull;
+                        const unsigned s = it % I8_STAGES, u = it / I8_STAGES;
+                        if (u > 0) mbar_wait(empty + 8 * s, (u - 1) & 1);
+                        mbar_expect_tx(full + 8 * s, I8_STAGE_BYTES);
+                        const unsigned dst = sbase + s * I8_STAGE_BYTES;
+                        bulk_g2s_mc(dst + rank * (4 * I8_A_BYTES), S + i8_tile_off(ks, ti, g.nblk) + rank * (4 * I8_A_BYTES), 4 * I8_A_BYTES,
+                                    full + 8 * s, (unsigned short)3);
+                        const signed char* bsrc = S + i8_tile_off(ks, tj, g.nblk) + h * I8_B_BYTES;
 #pragma unroll
-                    for (int sl = 0; sl < I8_NSL; ++sl)
-                        bulk_g2s(dst + I8_NSL * I8_A_BYTES + sl * I8_B_BYTES, bsrc + sl * I8_A_BYTES, I8_B_BYTES, full + 8 * s);
+                        for (int sl = 0; sl < I8_NSL; ++sl)
+                            bulk_g2s(dst + I8_NSL * I8_A_BYTES + sl * I8_B_BYTES, bsrc + sl * I8_A_BYTES, I8_B_BYTES, full + 8 * s);
+                        ++it;
+                    }
                 }
             }
         }
@@ -505,17 +529,26 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
         if (lane == 0) {
             const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TB >> 4) << 24);
             unsigned it = 0, tile = 0;
-            for (int w = cl; w < total; w += ncl, ++tile) {
+            for (int w = cl; w < total; w += ncl) {
+                int mat, ti, tj;
+                bool diag;
+                decode(w, mat, ti, tj, diag);
+                if (!i8_any_active(g, mat, ti, tj, nks)) continue;   // nothing but exact zeros to add: the tile is left alone
                 if (tile > 0) {                                     // the epilogue has drained the previous tile's accumulators
                     mbar_wait(tfree, (tile - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
-                for (int ks = 0; ks < nks; ++ks, ++it) {
+                bool first_step = true;
+                for (int wd = 0; wd * 64 < nks; ++wd) {
+                  unsigned long long act = i8_active_word(g, mat, ti, tj, wd, nks);
+                  while (act) {
+                    act &= act - 1ull;
                     const unsigned s = it % I8_STAGES;
                     mbar_wait(full + 8 * s, (it / I8_STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const unsigned a0 = sbase + s * I8_STAGE_BYTES, b0 = a0 + I8_NSL * I8_A_BYTES;
-                    const unsigned accum0 = ks > 0 ? 1u : 0u;
+                    const unsigned accum0 = first_step ? 0u : 1u;
+                    first_step = false;
                     I8_MMA(0, 0, 4, true);
                     I8_MMA(0, 4, 4, true);
                     I8_MMA(1, 0, 4, false);
@@ -529,8 +562,11 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
                     I8_MMA(6, 0, 2, false);
                     I8_MMA(7, 0, 1, false);
                     umma_commit_mc(empty + 8 * s, (unsigned short)3);
+                    ++it;
+                  }
                 }
                 umma_commit(done);
+                ++tile;
             }
         }
     } else {
@@ -545,10 +581,11 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
         double* cgen = reinterpret_cast<double*>(smem_raw + (crow - sraw));
         const unsigned tlane = tmem + ((unsigned)(q * 32) << 16);
         unsigned tile = 0;
-        for (int w = cl; w < total; w += ncl, ++tile) {
+        for (int w = cl; w < total; w += ncl) {
             int mat, ti, tj;
             bool diag;
             decode(w, mat, ti, tj, diag);
+            if (!i8_any_active(g, mat, ti, tj, nks)) continue;       // same decision as the producer and the MMA thread
             const bool half_tile = diag && h == 1;                  // rows 0..63 lie strictly above the diagonal
             const bool skip = half_tile && q < 2;                   // warp-uniform
             const double* esc = g.rscale + (size_t)mat * 2 * n + n;
@@ -601,6 +638,7 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tfree);
             }
+            ++tile;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
