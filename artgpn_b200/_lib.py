@@ -61,6 +61,7 @@ _SIGNATURES = {
     "agpn_update_path": (ctypes.c_int, [c_void_p]),
     "agpn_predict_path": (ctypes.c_int, [c_void_p]),
     "agpn_timeline_dump": (ctypes.c_int, [c_void_p, ctypes.c_char_p]),
+    "agpn_skip_stats": (ctypes.c_int, [c_void_p, c_void_p]),
     "agpn_mega_prof": (ctypes.c_int, [c_void_p, c_void_p]),
     "agpn_slice_ms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
 }

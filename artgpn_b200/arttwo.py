@@ -504,6 +504,14 @@ class network(object):
         INT8-sliced path (chosen at construction from AGPN_SYRK)."""
         return int(_lib.load().agpn_update_path(self._ctx()))
 
+    def skip_stats(self):
+        """(dense K steps, executed K steps, panel-solve tile halves, halves left out, right halves among them) of the last wave of
+        log_likelihood_batch: the INT8-sliced update leaves out K steps whose digit chunks are all zero (exact), the
+        panel solve the tile halves bounded below 2^-96 of their row scale."""
+        out = np.zeros(5)
+        _lib.check(_lib.load().agpn_skip_stats(self._ctx(), _lib.ptr(out)))
+        return tuple(float(v) for v in out)
+
     def predict_path(self):
         """1: the last prediction ran on the factorisation kernels (K* appended as block rows, INT8-sliced updates);
         0: on the stand-alone FP64 predict_kernel (AGPN_PREDICT=dmma or automatic fall-back); -1: none yet."""

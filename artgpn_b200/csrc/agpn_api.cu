@@ -174,6 +174,10 @@ struct agpn_ctx {
     bool i8_skip = true;
     unsigned long long* d_nzmask = nullptr;     // [cap_mats][nblk][nzwords]
     int nzwords = 0;
+    bool trsm_skip = true;                      // AGPN_TRSM_SKIP=0: panel solves never leave a negligible tile half out
+    double* d_linvnorm = nullptr;               // [cap_mats][linv_blocks][2]
+    int mask_nmat = 0;                          // matrices of the last wave that ran with masks (0: it ran dense)
+    int wave_nmat = 0;                          // matrices of the last wave
     // panel solves with one CTA per 64-column half of a tile (AGPN_TRSM_SPLIT=0: one CTA per tile)
     bool trsm_split = true;
     double* d_rslot = nullptr;     // [cap_mats][nblk][2][2][128] parked forward-solve sums of the split panel solves
@@ -301,6 +305,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_MEGA")) c->use_mega = atoi(e) != 0;
     if (const char* e = getenv("AGPN_TRSM_SPLIT")) c->trsm_split = atoi(e) != 0;
     if (const char* e = getenv("AGPN_I8_SKIP")) c->i8_skip = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_TRSM_SKIP")) c->trsm_skip = atoi(e) != 0;
     if (const char* e = getenv("AGPN_MEGA_PROF")) if (atoi(e) != 0) {
         if (cudaMalloc(&c->d_megaprof, sizeof(unsigned long long) * 16 * 2 * c->i8_clusters_max) != cudaSuccess) { cudaGetLastError(); c->d_megaprof = nullptr; }
     }
@@ -386,7 +391,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_S8); cudaFree(c->d_rscale);
     cudaFree(c->d_paug); cudaFree(c->d_ps8); cudaFree(c->d_pvec);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
-    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot); cudaFree(c->d_nzmask);
+    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot); cudaFree(c->d_nzmask); cudaFree(c->d_linvnorm);
     agpn_comm_release(c);
     delete c;
     return 0;
@@ -473,6 +478,42 @@ extern "C" int agpn_slice_ms(agpn_ctx* c, double* ms, long long* launches) {
 
 // AGPN_TIMELINE=1 diagnostics: start / end (ms after the first launch of the call) of every launch of the last
 // agpn_loglike_batch, with its phase and sub-batch stream -- the concurrency picture of the sub-batch streams
+// Work the last wave of agpn_loglike_batch actually executed on the INT8 path (read back from the zero-chunk masks):
+// out[0] K steps (128 x 128 x 32, all 36 slice pairs) a dense schedule runs, out[1] K steps executed,
+// out[2] panel-solve tile halves, out[3] of them left out by the bound test, out[4] the right (K = 128) halves among those.
+// Dense run: out[1] = out[0], out[3] = out[4] = 0.
+extern "C" int agpn_skip_stats(agpn_ctx* c, double* out) {
+    if (!c || !out) USAGE_FAIL("agpn_skip_stats: null pointer");
+    ENTER_DEVICE(c->device);
+    const int nb = c->nblk, nm = c->mask_nmat;
+    double nominal = 0.0, halves = 0.0;
+    for (int k = 0; k < nb; ++k) {
+        nominal += 4.0 * k * (nb - k);
+        halves += 2.0 * (nb - k - 1);
+    }
+    if (nm == 0 || !c->d_nzmask) {
+        out[0] = out[1] = nominal * c->wave_nmat; out[2] = halves * c->wave_nmat; out[3] = out[4] = 0.0;
+        return 0;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    const size_t words = (size_t)nm * nb * c->nzwords;
+    std::vector<unsigned long long> h(words + 2);
+    CUDA_TRY(cudaMemcpy(h.data(), c->d_nzmask, sizeof(unsigned long long) * words, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&h[words], c->d_nzmask + (size_t)c->cap_mats * nb * c->nzwords, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    double active = 0.0;
+    for (int m = 0; m < nm; ++m)
+        for (int k = 1; k < nb; ++k)
+            for (int ti = k; ti < nb; ++ti)
+                for (int w = 0; w * 64 < 4 * k; ++w) {
+                    unsigned long long a = h[((size_t)m * nb + ti) * c->nzwords + w] & h[((size_t)m * nb + k) * c->nzwords + w];
+                    const int rem = 4 * k - 64 * w;
+                    if (rem < 64) a &= (1ull << rem) - 1ull;
+                    active += (double)__builtin_popcountll(a);
+                }
+    out[0] = nominal * nm; out[1] = active; out[2] = halves * nm; out[3] = (double)(h[words] + h[words + 1]); out[4] = (double)h[words + 1];
+    return 0;
+}
+
 extern "C" int agpn_timeline_dump(agpn_ctx* c, const char* path) {
     if (!c || !path) USAGE_FAIL("agpn_timeline_dump: null pointer");
     if (!c->timeline || c->timeline_used == 0) USAGE_FAIL("agpn_timeline_dump: no timeline (create the context with AGPN_TIMELINE=1)");
@@ -599,11 +640,14 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 4 * nmat));
         cudaFree(c->d_nzmask);
+        cudaFree(c->d_linvnorm);
         c->d_nzmask = nullptr;
+        c->d_linvnorm = nullptr;
         if (c->i8_skip && c->fuse_slices && c->i8_which && c->nblk > 2) {
             const int sg = c->i8_group < 2 ? 2 : c->i8_group;
             c->nzwords = (4 * sg + 63) / 64;
-            CUDA_TRY(cudaMalloc(&c->d_nzmask, sizeof(unsigned long long) * nmat * c->nblk * c->nzwords));
+            CUDA_TRY(cudaMalloc(&c->d_nzmask, sizeof(unsigned long long) * (nmat * c->nblk * c->nzwords + 2)));   // + 2 counters
+            if (c->trsm_skip) CUDA_TRY(cudaMalloc(&c->d_linvnorm, sizeof(double) * nmat * c->linv_blocks * 2));
         }
         cudaFree(c->d_rslot);
         c->d_rslot = nullptr;
@@ -882,10 +926,16 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         // so every launch can be split (the task kernel keeps one CTA group per tile)
         const bool mega_wave = mega_eligible(c) && c->d_mega && !c->profiling && !c->timeline;
         if (c->trsm_split && c->d_rslot && c->i8_which == 3 && c->fuse_slices && c->i8_group >= c->nblk && !mega_wave) g.rslot = c->d_rslot;
-        if (c->d_nzmask && c->i8_group >= c->nblk) {
+        c->mask_nmat = 0;
+        c->wave_nmat = (int)nmat;
+        if (c->d_nzmask && c->i8_group >= c->nblk && !mega_wave) {
             // masks are rebuilt by every wave's panel solves (one group of all block columns: kc32 = 4 k + chunk)
             g.nzmask = c->d_nzmask; g.nzwords = c->nzwords;
+            g.linvnorm = c->d_linvnorm;
+            g.nzstat = c->d_nzmask + (size_t)c->cap_mats * c->nblk * c->nzwords;
+            c->mask_nmat = (int)nmat;
             CUDA_TRY(cudaMemsetAsync(c->d_nzmask, 0, sizeof(unsigned long long) * (size_t)nmat * c->nblk * c->nzwords, st));
+            CUDA_TRY(cudaMemsetAsync(g.nzstat, 0, 2 * sizeof(unsigned long long), st));
         }
         PhaseScope ps(c, st, PH_SLICE, cur);
         i8_rowscale_kernel<<<dim3((c->npad + 255) / 256, nmat), 256, 0, st>>>(g, c->npad, nullptr, 0);
@@ -920,6 +970,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             gs.refine = g.refine + (size_t)m0 * g.refine_blocks;
             if (g.rslot) gs.rslot = g.rslot + rslot_off(g.nblk, m0, 0, 0, 0);
             if (g.nzmask) gs.nzmask = g.nzmask + (size_t)m0 * g.nblk * g.nzwords;
+            if (g.linvnorm) gs.linvnorm = g.linvnorm + (size_t)m0 * g.linv_blocks * 2;
             gs.nmat = m1 - m0;
             gs.mat0 = m0;
             if (g.S8) {

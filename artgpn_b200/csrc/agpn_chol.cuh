@@ -76,7 +76,14 @@ struct CholArgs {
     // are bit-identical to the dense schedule.  nullptr: dense.
     unsigned long long* nzmask = nullptr;
     int nzwords = 0;
+    // inf-norms of the two 64-row halves of Linv_kk, written by potrf_diag_kernel: [nmat][linv_blocks][2].  With the masks
+    // above, trsm_kernel first bounds its result |X_ic| <= max_j |C_ij| * ||Linv half||_inf and leaves the tile half out
+    // (no GEMM, no digits, no forward-solve sum, mask bits stay clear) when every entry is below 2^-40 of one digit unit
+    // -- below 2^-96 of its row scale, 2^-43 of an ulp of anything it could be added to.  nullptr: never.
+    double* linvnorm = nullptr;
+    unsigned long long* nzstat = nullptr;       // or nullptr: tile halves left out, [0] left (K = 64) and [1] right (K = 128) halves (agpn_skip_stats)
 };
+#define TRSM_SKIP_BOUND 9.094947017729282e-13      /* 2^-40 */
 __host__ __device__ __forceinline__ size_t rslot_off(int nblk, int mat, int ti, int parity, int h) {
     return ((((size_t)mat * nblk + ti) * 2 + parity) * 2 + h) * 128;
 }
@@ -499,8 +506,46 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
         }
     }
     grp_sync<G>();
+    bool skip = false;
+    if (g.linvnorm != nullptr && g.nzmask != nullptr && (flags & 3) == 3 && !refine) {
+        // bound the half (split) or the tile before touching the tensor pipe
+        const double* ln = g.linvnorm + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * 2;
+        const double lnorm = hsel >= 0 ? ln[hsel] : fmax(ln[0], ln[1]);
+        // warp w scans rows 16 w .. 16 w + 15, a row's columns spread over the lanes (coalesced), eight rows in flight
+        const int nld = hsel == 0 ? 1 : 2;                      // double2 loads per lane and row: 64 or 128 input columns
+        const double thr = TRSM_SKIP_BOUND / lnorm;              // lnorm inf / NaN: nothing passes
+        int bad = 0;
+#pragma unroll
+        for (int r8 = 0; r8 < 2; ++r8) {
+            double2 v[8][2];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double* src = Aik + (size_t)(warp * 16 + r8 * 8 + r) * ld;
+                v[r][0] = *reinterpret_cast<const double2*>(src + 2 * lane);
+                v[r][1] = nld == 2 ? *reinterpret_cast<const double2*>(src + 64 + 2 * lane) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                // the sum bounds the maximum and, unlike fmax, keeps a NaN
+                const double m = (fabs(v[r][0].x) + fabs(v[r][0].y)) + (fabs(v[r][1].x) + fabs(v[r][1].y));
+                bad |= !(m * qs[warp * 16 + r8 * 8 + r] < thr);   // NaN / inf count as "solve it"
+            }
+        }
+        if constexpr (!G) {
+            skip = __syncthreads_or(bad) == 0;
+        } else {
+            if (tid == 0) s_nz[0] = 0;
+            grp_sync<G>();
+            if (bad) s_nz[0] = 1;
+            grp_sync<G>();
+            skip = s_nz[0] == 0;
+            grp_sync<G>();
+        }
+        if (skip && tid == 0 && g.nzstat != nullptr) atomicAdd(g.nzstat + (hsel == 0 ? 0 : 1), hsel >= 0 ? 1ull : 2ull);
+    }
     double part[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][4][2];
+    if (!skip)
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         const int h = 1 - pass;
@@ -553,14 +598,15 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
                 for (int ni = 0; ni < 4; ++ni) {
                     unsigned piece[I8_NSL];
                     const double x0 = acc[mi][ni][0] * f, x1 = acc[mi][ni][1] * f;
-                    if (check_wrap && fmax(fabs(x0), fabs(x1)) > I8_QMAXF) wrapped = 1;
+                    const double xm = fmax(fabs(x0), fabs(x1));
+                    if (check_wrap && xm > I8_QMAXF) wrapped = 1;
+                    if (xm > 0.5) nzbits = 1;                    // rint(x) != 0 (ties go to the even 0): some digit is non-zero
                     i8_digits2(x0, x1, piece);
                     unsigned char* dst = stg + wn * I8_TILE_BYTES + (wm * 4 + mi) * 256 + (ni >> 1) * 128 + (lane >> 2) * 16 +
                                          (ni & 1) * 8 + 2 * (lane & 3);
 #pragma unroll
                     for (int sl = 0; sl < I8_NSL; ++sl) {
                         *reinterpret_cast<unsigned short*>(dst + sl * (TB * 32)) = (unsigned short)piece[sl];
-                        nzbits |= piece[sl];
                     }
                 }
             }
@@ -714,6 +760,8 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
     double* scr = Dv + 8 * 16 * PD_DV_LD;      // [8][16][20] per-warp scratch
     __shared__ int s_fail;
     __shared__ int s_refine;
+    __shared__ double s_ln_[G ? 2 : 1][4];
+    double* s_ln = s_ln_[grp_id<G>()];
 
     const int tid = grp_tid<G>(), lane = tid & 31, warp = tid >> 5;
     const int ld = g.ld;
@@ -960,13 +1008,30 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
         if (tid < TB) {
             const int R = tid;
             const int b0 = (R >> 4) * 16;
-            double sacc = 0.0;
-            for (int C = 0; C < b0; ++C) sacc = fma(S[C * PD_LD + R], zs[C], sacc);
-            for (int C = b0; C <= R; ++C) sacc = fma(Dv[(R >> 4) * 16 * PD_DV_LD + (R & 15) * PD_DV_LD + (C - b0)], zs[C], sacc);
+            double sacc = 0.0, asum = 0.0;                       // asum: the row's absolute sum (inf-norm of the inverse, for trsm's skip test)
+            for (int C = 0; C < b0; ++C) {
+                const double v = S[C * PD_LD + R];
+                sacc = fma(v, zs[C], sacc);
+                asum += fabs(v);
+            }
+            for (int C = b0; C <= R; ++C) {
+                const double v = Dv[(R >> 4) * 16 * PD_DV_LD + (R & 15) * PD_DV_LD + (C - b0)];
+                sacc = fma(v, zs[C], sacc);
+                asum += fabs(v);
+            }
             zout[R] = sacc;
             rhs[R] = sacc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) asum = fmax(asum, __shfl_xor_sync(0xffffffffu, asum, o));
+            if ((tid & 31) == 0) s_ln[tid >> 5] = asum;
         }
         grp_sync<G>();
+    }
+    if (g.linvnorm != nullptr && tid < 2) {
+        // inf-norm of the two 64-row halves of the inverse; infinity (never skip) when it was not formed above
+        const bool have = rhs != nullptr && !s_refine;
+        g.linvnorm[((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * 2 + tid] =
+            have ? fmax(s_ln[2 * tid], s_ln[2 * tid + 1]) : __longlong_as_double(0x7ff0000000000000ll);
     }
     if (tid < 32) {
         double qv = 0.0, lv = 0.0;

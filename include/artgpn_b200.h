@@ -253,6 +253,15 @@ int agpn_slice_ms(agpn_ctx* ctx, double* ms, long long* launches);
 /* Diagnostics (context created with AGPN_TIMELINE=1 in the environment): CSV of start / end times, phase and sub-batch
  * stream of every launch of the last agpn_loglike_batch, measured WITHOUT serialising the streams. */
 int agpn_timeline_dump(agpn_ctx* ctx, const char* path);
+/* Work the last wave of agpn_loglike_batch executed on the INT8-sliced path.  The factor of a covariance whose correlation
+ * length is short against the time span is numerically banded: panel entries below 2^-57 of their row scale have all eight
+ * digits zero, and a K step in which either operand chunk is all-zero adds exact integer zeros -- the update leaves it out
+ * (bit-identical results; AGPN_I8_SKIP=0 runs the dense schedule).  Panel-solve tile halves whose entries are bounded below
+ * 2^-96 of their row scale are left out too (AGPN_TRSM_SKIP=0: never).
+ * out[0] = K steps (128 x 128 x 32, 36 slice pairs each) of the dense schedule, out[1] = K steps executed,
+ * out[2] = panel-solve tile halves, out[3] = halves left out, out[4] = the right (K = 128) halves among them (out: 5 doubles).
+ * No reference counterpart (np.linalg / LAPACK is dense). */
+int agpn_skip_stats(agpn_ctx* ctx, double* out);
 /* Diagnostics (AGPN_MEGA_PROF=1): per-CTA means of the persistent task kernel's time slots of the last wave, in
  * microseconds (slots 1, 4, 7 are task counts): 0 update runs, 1 update tasks, 2 diagonal-block bodies, 3 their waits,
  * 4 diagonal-block tasks, 5 panel-solve bodies, 6 their waits, 7 panel-solve tasks (thread group 0), 8 whole kernel,

@@ -340,3 +340,74 @@ def test_sample_from_a_multi_block_covariance():
     exp = z @ np.linalg.cholesky(K).T
     assert np.max(np.abs(got - exp)) <= 1e-10 * np.max(np.abs(exp))
     net.close()
+
+
+# ---- banded digit planes: K steps / tile halves with nothing but zero digits are left out --------------------------
+def _ll_with_env(monkeypatch, env, N, theta, p=3, q=2, weights="Constant", stats=False):
+    from artgpn_b200 import synth, node, weight, mean
+    for k in ("AGPN_I8_SKIP", "AGPN_TRSM_SKIP"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    net, data = _net(N, p, q)
+    net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], p, q, weights)[:3])
+    out = net.log_likelihood_batch(theta)
+    assert np.array_equal(out, net.log_likelihood_batch(theta))
+    st = net.skip_stats()
+    net.close()
+    for k in env:
+        monkeypatch.delenv(k, raising=False)
+    return (out, st, data) if stats else out
+
+
+def test_zero_chunk_skipping_is_bit_identical_to_the_dense_schedule(monkeypatch):
+    """Short correlation lengths (the BASELINE workload): most K steps of the trailing update and about two fifths of the
+    panel-solve tile halves hold only zero digits and are left out.  Leaving out K steps is exact; the panel-solve bound
+    sits 2^-40 below one digit unit, and the log-likelihoods come out bit-identical to the dense schedule."""
+    from artgpn_b200 import synth
+    N = 1900
+    theta = synth.make_walkers(6, p=3, q=2, seed=1)
+    dense, st_d, (t, y, sig) = _ll_with_env(monkeypatch, {"AGPN_I8_SKIP": "0"}, N, theta, stats=True)
+    assert st_d[1] == st_d[0] and st_d[3] == 0
+    usk, st_u, _ = _ll_with_env(monkeypatch, {"AGPN_TRSM_SKIP": "0"}, N, theta, stats=True)
+    assert np.array_equal(usk, dense)
+    assert st_u[0] == st_d[0] and st_u[1] < 0.5 * st_u[0] and st_u[3] == 0, st_u
+    both, st_b, _ = _ll_with_env(monkeypatch, {}, N, theta, stats=True)
+    assert np.array_equal(both, dense)
+    assert st_b[1] == st_u[1], (st_b, st_u)                    # the halves left out had no non-zero digit anyway
+    assert 0.2 * st_b[2] < st_b[3] < 0.6 * st_b[2], st_b
+    m = _Spec()
+    exp = oracle.log_likelihood(t, y, sig, 2, *synth.objects_from_row(m, m, m, theta[1], 3, 2))
+    assert abs(both[1] - exp) <= 1e-9 * abs(exp)
+
+
+def test_nothing_is_skipped_when_the_covariance_does_not_decay(monkeypatch):
+    """Periodic nodes never decay: every chunk holds non-zero digits, the masks are all ones, no work is left out."""
+    from artgpn_b200 import synth, node, weight, mean
+    N = 1100
+    net, (t, y, sig) = _net(N, 2, 2)
+    nodes = [node.Periodic(31.0, 1.1), node.Periodic(47.0, 0.9)]
+    weights = [weight.Constant(1.3), weight.Constant(0.8), weight.Constant(0.7), weight.Constant(1.1)]
+    means = [mean.Constant(0.1), mean.Constant(-0.2)]
+    jitters = [0.3, 0.4]
+    ll = net.log_likelihood(nodes, weights, means, jitters)
+    st = net.skip_stats()
+    net.close()
+    assert st[1] == st[0] and st[3] == 0, st
+    m = _Spec()
+    exp = oracle.log_likelihood(t, y, sig, 2, [m.Periodic(31.0, 1.1), m.Periodic(47.0, 0.9)],
+                                [m.Constant(1.3), m.Constant(0.8), m.Constant(0.7), m.Constant(1.1)],
+                                [m.Constant(0.1), m.Constant(-0.2)], jitters)
+    assert abs(ll - exp) <= 1e-9 * abs(exp)
+
+
+def test_skipping_with_sub_batch_streams(monkeypatch):
+    """144 matrices run as four sub-batches on their own streams, each with its slice of the masks and inverse norms:
+    same bits as the dense schedule."""
+    from artgpn_b200 import synth
+    N = 700
+    theta = synth.make_walkers(48, p=3, q=2, seed=3)
+    out, st, _ = _ll_with_env(monkeypatch, {}, N, theta, stats=True)
+    dense = _ll_with_env(monkeypatch, {"AGPN_I8_SKIP": "0"}, N, theta)
+    assert np.array_equal(out, dense)
+    assert st[1] < st[0]
