@@ -15,10 +15,15 @@ partitioned over the GPUs (strong scaling: BASELINE config 3 is "128 walkers at 
            per step (agpn_loglike_batch_sharded: local rows + one ncclAllGather).
 `e2e`    : evals/s through network.log_likelihood_batch(host numpy theta) -- H2D of theta and
            D2H of the results inside the timed region.
-`roofline`: the dominant kernel -- the trailing update.  Default path: syrk_i8_persistent_kernel, exact integer
-           products of 7-bit slices on the INT8 tensor path (tcgen05.mma.kind::i8), executed INT8 ops against the
-           kind::i8 issue peak measured in this run (agpn_i8_peak); with AGPN_SYRK=dmma: syrk_kernel against the
-           FP64 tensor (DMMA.8x8x4) issue peak measured in this run.
+`roofline`: the kernel with the largest share of the step.  On the default path that is either the panel solve
+           (trsm_kernel: DMMA.8x8x4 GEMM against the explicit inverse with digit extraction fused; executed flops
+           against the FP64 tensor issue peak measured in this run) or the trailing update (syrk_i8_persistent_kernel:
+           exact integer products of 7-bit slices on tcgen05.mma.kind::i8; EXECUTED INT8 ops against the kind::i8
+           issue peak measured in this run); the other one is reported as `roofline_update` / `roofline_panel_solve`.
+           Both kernels leave out work that is exactly / provably nothing: K steps whose digit chunks are all zero,
+           panel tile halves bounded below 2^-96 of their row scale.  Only executed work is counted; the fraction is
+           in the object, and `dense_schedule` (extras) times the same step with nothing left out.
+           With AGPN_SYRK=dmma: syrk_kernel against the FP64 tensor (DMMA.8x8x4) issue peak.
 `roofline_cholesky`: the whole batched Cholesky, ALGORITHMIC FP64 flops p N^3 / 3 per eval against the DMMA.8x8x4 peak
            (BASELINE's "% FP64 TC peak"; above 1.0 on the INT8-sliced path).  `roofline_dmma_path`: the same figure
            with every kernel of the factorisation on the FP64 tensor instruction (second context, AGPN_SYRK=dmma).
@@ -387,6 +392,7 @@ def main():
 
     phase, nl, slice_ms, slice_n = profiled(net, theta_d)
     update_path = net.update_path()
+    skip = net.skip_stats()          # (dense K steps, executed K steps, panel tile halves, halves left out, right halves among them)
     p, N = cfg["p"], cfg["N"]
     peaks, peak_src = load_peaks()
 
@@ -423,6 +429,25 @@ def main():
             "max_rel_diff_vs_default_path": agree,
             "note": "ALGORITHMIC flops p N^3 / 3 per eval over the device time of the factorisation kernels; the north_star's "
                     "'>= 50 % of FP64 tensor-core peak on the batched Cholesky' on the path that uses only the FP64 tensor instruction"}
+
+        # (a2) the dense schedule: no K step / tile half left out (what a covariance that does not decay would cost)
+        dense_extra = None
+        if update_path:                      # same decision on every rank (timed() holds barriers)
+            os.environ["AGPN_I8_SKIP"] = "0"
+            try:
+                net_n, _ = make_net(cfg)
+                net_n._ctx()
+            finally:
+                os.environ.pop("AGPN_I8_SKIP", None)
+            net_n.set_structure(*o[:3])
+            ms_n, out_n = timed(lambda: net_n.log_likelihood_batch(theta_d), 5, 3)
+            ph_n, _, _, _ = profiled(net_n, theta_d)
+            dense_extra = {"what": "AGPN_I8_SKIP=0, second context: every K step and every panel-solve tile executed",
+                           "ms_per_step": ms_n, "evals_per_s": W_total / (ms_n * 1e-3),
+                           "phase_ms": {"potrf_diag": float(ph_n[2]), "trsm": float(ph_n[3]), "syrk": float(ph_n[4])},
+                           "bit_identical_to_the_default_schedule": bool(np.array_equal(out_n.cpu().numpy(), result_host[lo:hi]))}
+            net_n.close()
+            extra_out["dense_schedule"] = dense_extra
 
         # (b) 16-walker single-GPU latency (the reference's own caller runs half-ensembles of 15, 01_emcee.py:111-122)
         th16 = torch.from_numpy(np.ascontiguousarray(theta_all[:16])).to(dev)
@@ -533,14 +558,21 @@ def main():
         except Exception:
             pass
         dmma_peak = float(peak_tf[0])
+        second_roofline = None
         syrk_share = float(phase[4] / max(step_prof_ms, 1e-9))
         if update_path:
             i8_peak = np.zeros(1)
             _lib.check(lib.agpn_i8_peak(local_rank, _lib.ptr(i8_peak)))
             i8_peak = float(i8_peak[0])
-            # 36 slice pairs (s + t <= 7) per FP64 product, 2 ops per int8 multiply-add
-            syrk_tops = 36.0 * syrk_tf if syrk_tf else None
-            roofline = {
+            # 36 slice pairs (s + t <= 7) per FP64 product, 2 ops per int8 multiply-add.  EXECUTED ops: the kernel leaves out
+            # the K steps (128 x 128 x 32) in which either operand's digit chunk is all zero (exact), so the dense count is
+            # scaled by the fraction of K steps the masks of this run's last wave let through (agpn_skip_stats)
+            active = skip[1] / skip[0] if skip[0] > 0 else 1.0
+            dense_ops = 36.0 * W_local * p * syrk_tiles * 2.0 * 128 ** 3
+            exec_ops = dense_ops * active
+            syrk_tops = exec_ops / (phase[4] * 1e-3) / 1e12 if phase[4] > 0 else None
+            syrk_tf_exec = syrk_tf * active if syrk_tf else None
+            roofline_update = {
                 "bound": "tensor",
                 "kernel": "syrk_i8_persistent_kernel: trailing update as exact integer products of 8 x 7-bit slices, "
                           "tcgen05.mma.kind::i8 with TMEM int32 accumulators (all launches of a step)",
@@ -549,14 +581,35 @@ def main():
                 "peak_source": "kind::i8 issue peak (M=128, N=256, operands resident in shared memory) measured in this run "
                                "(agpn_i8_peak); MEASURED_PEAKS.json has no INT8 figure (2 x its bf16 burst = %.0f TOP/s)"
                                % (2.0 * peaks.get("bf16_tflops", float("nan"))),
-                "ops_per_step": (36.0 * W_local * p * syrk_tiles * 2.0 * 128 ** 3),
+                "ops_per_step": exec_ops, "dense_ops_per_step": dense_ops, "active_k_step_fraction": active,
                 "ms": float(phase[4]), "launches": int(nl[4]), "share_of_step_ms": syrk_share,
                 "traffic": syrk_traffic,
                 "traffic_note": "DRAM bytes of all syrk_i8_persistent_kernel launches of one step, ncu pass in profiles/ (scaled by walkers)",
-                "fp64_equivalent": {"tflops": syrk_tf, "dmma_peak_tflops": dmma_peak,
-                                    "ratio_to_dmma_peak": (syrk_tf / dmma_peak) if syrk_tf else None,
-                                    "note": "the same update on the FP64 tensor instruction cannot exceed 1.0"},
-                "note": "executed ops (full diagonal tiles counted), CUDA-event time of the launches in a profiled pass"}
+                "fp64_equivalent": {"tflops_executed": syrk_tf_exec, "tflops_dense_schedule_equivalent": syrk_tf,
+                                    "dmma_peak_tflops": dmma_peak,
+                                    "note": "the same update on the FP64 tensor instruction cannot exceed the DMMA peak"},
+                "note": "EXECUTED ops only (full diagonal tiles counted): K steps whose operand digit chunks are all zero are "
+                        "left out -- exact, the results are bit-identical to the dense schedule (extras: dense_schedule); "
+                        "CUDA-event time of the launches in a profiled pass"}
+            # the panel solve: executed DMMA flops of the tile halves that were solved (right half K = 128, left half K = 64)
+            halves = skip[2] / 2.0
+            scale = W_local * p / (skip[2] / (2.0 * sum(nblk - k - 1 for k in range(nblk)))) if skip[2] > 0 else 1.0
+            right_done, left_done = halves - skip[4], halves - (skip[3] - skip[4])
+            trsm_flops = scale * (right_done * 2.0 * 128 * 64 * 128 + left_done * 2.0 * 128 * 64 * 64)
+            trsm_tf = trsm_flops / (phase[3] * 1e-3) / 1e12 if phase[3] > 0 else None
+            roofline_panel = {
+                "bound": "tensor",
+                "kernel": "trsm_kernel: A_ik Linv_kk^T on DMMA.8x8x4, digit extraction and plane stores fused (all launches of a step)",
+                "achieved": trsm_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": (trsm_tf / dmma_peak) if trsm_tf else None,
+                "peak_source": "DMMA.8x8x4 issue peak measured in this run (agpn_dmma_peak); MEASURED_PEAKS.json has no FP64 figure",
+                "flops_per_step": trsm_flops, "tile_halves": skip[2] * scale, "tile_halves_left_out": skip[3] * scale,
+                "ms": float(phase[3]), "launches": int(nl[3]), "share_of_step_ms": float(phase[3] / max(step_prof_ms, 1e-9)),
+                "traffic": None,
+                "note": "EXECUTED GEMM flops of the halves that were solved; halves whose entries are bounded below 2^-96 of "
+                        "their row scale are left out after a read-only bound pass (AGPN_TRSM_SKIP=0: none)"}
+            # `roofline` = the kernel with the largest share of the step
+            roofline = roofline_panel if phase[3] > phase[4] else roofline_update
+            second_roofline = ("roofline_update", roofline_update) if roofline is roofline_panel else ("roofline_panel_solve", roofline_panel)
         else:
             roofline = {
                 "bound": "tensor", "kernel": "syrk_kernel (DMMA.8x8x4; all narrow + wide launches of a step)",
@@ -594,6 +647,8 @@ def main():
                          "trsm": float(phase[3]), "syrk": float(phase[4]), "finalize": float(phase[5]),
                          "digit_slicing": float(slice_ms), "launches": [int(x) for x in nl] + [int(slice_n)]},
         }
+        if second_roofline is not None:
+            line[second_roofline[0]] = second_roofline[1]
         if cpu_base is not None:
             ref_vals = np.array(cpu_base.pop("_vals"))
             got = result_host[:len(ref_vals)]
