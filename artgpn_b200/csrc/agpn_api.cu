@@ -176,6 +176,8 @@ struct agpn_ctx {
     int nzwords = 0;
     bool trsm_skip = true;                      // AGPN_TRSM_SKIP=0: panel solves never leave a negligible tile half out
     double* d_linvnorm = nullptr;               // [cap_mats][linv_blocks][2]
+    unsigned long long* d_pmask = nullptr;      // prediction: masks of the stacked factor | 2 counters | 2 inverse norms
+    size_t cap_pmask = 0;
     int mask_nmat = 0;                          // matrices of the last wave that ran with masks (0: it ran dense)
     int wave_nmat = 0;                          // matrices of the last wave
     // panel solves with one CTA per 64-column half of a tile (AGPN_TRSM_SPLIT=0: one CTA per tile)
@@ -391,7 +393,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_S8); cudaFree(c->d_rscale);
     cudaFree(c->d_paug); cudaFree(c->d_ps8); cudaFree(c->d_pvec);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
-    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot); cudaFree(c->d_nzmask); cudaFree(c->d_linvnorm);
+    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot); cudaFree(c->d_nzmask); cudaFree(c->d_linvnorm); cudaFree(c->d_pmask);
     agpn_comm_release(c);
     delete c;
     return 0;
@@ -715,6 +717,15 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
     // remaining trailing block then holds the Schur complement (used for the predictive covariance)
     if (kstop < 0 || kstop > g.nblk) kstop = g.nblk;
     const int i8 = (g.S8 && group <= g.sgroup) ? c->i8_which : 0;
+    // the zero-chunk masks are indexed from block column 0 and only the persistent update kernel reads them: one group,
+    // fused digit extraction, persistent clusters -- otherwise everything runs dense (a panel tile left out by the bound
+    // test would leave stale digit planes behind for a kernel that does not look at the masks)
+    if (g.nzmask != nullptr && !(i8 != 0 && c->i8_persist && c->fuse_slices && group >= kstop)) {
+        g.nzmask = nullptr;
+        g.linvnorm = nullptr;
+        g.nzstat = nullptr;
+        c->mask_nmat = 0;
+    }
     for (int k0 = 0; k0 < kstop; k0 += group) {
         const int kend = (k0 + group < kstop) ? k0 + group : kstop;
         for (int k = k0; k < kend; ++k) {
@@ -1454,6 +1465,16 @@ static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, int grid
         if (cudaMalloc(&c->d_pvec, sizeof(double) * (3 * T + 2)) != cudaSuccess) { cudaGetLastError(); *unavailable = 1; return 0; }
         c->cap_pvec = 3 * T + 2;
     }
+    // zero-chunk masks of the stacked factor's row tiles (+ 2 counters) and the inverse norms of the current diagonal block
+    const int nzwords = (4 * sgroup + 63) / 64;
+    const size_t mask_words = (size_t)nrt * nzwords + 2 + 2;    // masks | counters | 2 doubles
+    if (c->i8_skip && c->nblk > 1 && mask_words > c->cap_pmask) {
+        cudaFree(c->d_pmask);
+        c->d_pmask = nullptr;
+        c->cap_pmask = 0;
+        if (cudaMalloc(&c->d_pmask, sizeof(unsigned long long) * mask_words) != cudaSuccess) { cudaGetLastError(); *unavailable = 1; return 0; }
+        c->cap_pmask = mask_words;
+    }
     double* d_rhs = c->d_pvec;                  // [T]: residual | 0  ->  z | -K* K^-1 r
     double* d_rs = c->d_pvec + T;               // [2][T] row scales
     int* d_flag = reinterpret_cast<int*>(c->d_pvec + 3 * T);
@@ -1483,6 +1504,13 @@ static int predict_stacked(agpn_ctx* c, int series, int M, size_t Mpad, int grid
     g.keep_factor = 1;                          // V is read back for the row sums of squares
     if (c->nblk > 1) {
         g.S8 = c->d_ps8; g.rscale = d_rs; g.sgroup = sgroup; g.i8flag = d_flag;
+        if (c->i8_skip && c->d_pmask && c->fuse_slices) {
+            // K* is banded too (a grid point far from every training time adds nothing): the same masks, the same bound test
+            g.nzmask = c->d_pmask; g.nzwords = nzwords;
+            g.nzstat = c->d_pmask + (size_t)nrt * nzwords;
+            if (c->trsm_skip) g.linvnorm = reinterpret_cast<double*>(c->d_pmask + (size_t)nrt * nzwords + 2);
+            CUDA_TRY(cudaMemsetAsync(c->d_pmask, 0, sizeof(unsigned long long) * mask_words, st));
+        }
         i8_rowscale_kernel<<<dim3((unsigned)((T + 255) / 256), 1), 256, 0, st>>>(g, c->npad, d_kss, c->predict_test_wrap ? 0 : M);
         LAUNCH_CHECK();
     }

@@ -78,8 +78,9 @@ struct CholArgs {
     int nzwords = 0;
     // inf-norms of the two 64-row halves of Linv_kk, written by potrf_diag_kernel: [nmat][linv_blocks][2].  With the masks
     // above, trsm_kernel first bounds its result |X_ic| <= max_j |C_ij| * ||Linv half||_inf and leaves the tile half out
-    // (no GEMM, no digits, no forward-solve sum, mask bits stay clear) when every entry is below 2^-40 of one digit unit
-    // -- below 2^-96 of its row scale, 2^-43 of an ulp of anything it could be added to.  nullptr: never.
+    // (no GEMM, no digits, no forward-solve sum, mask bits stay clear; zeros if the FP64 panel is kept) when every entry is
+    // below 2^-40 of one digit unit -- below 2^-96 of its row scale, 2^-43 of an ulp of anything it could be added to.
+    // nullptr: never.
     double* linvnorm = nullptr;
     unsigned long long* nzstat = nullptr;       // or nullptr: tile halves left out, [0] left (K = 64) and [1] right (K = 128) halves (agpn_skip_stats)
 };
@@ -507,7 +508,7 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
     }
     grp_sync<G>();
     bool skip = false;
-    if (g.linvnorm != nullptr && g.nzmask != nullptr && (flags & 3) == 3 && !refine) {
+    if (g.linvnorm != nullptr && g.nzmask != nullptr && (flags & 1) && !refine) {
         // bound the half (split) or the tile before touching the tensor pipe
         const double* ln = g.linvnorm + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * 2;
         const double lnorm = hsel >= 0 ? ln[hsel] : fmax(ln[0], ln[1]);
@@ -542,6 +543,14 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
             grp_sync<G>();
         }
         if (skip && tid == 0 && g.nzstat != nullptr) atomicAdd(g.nzstat + (hsel == 0 ? 0 : 1), hsel >= 0 ? 1ull : 2ull);
+        if (skip && !(flags & 2)) {
+            // the FP64 panel is kept (prediction reads V back): the tile's entries, below 2^-96 of their row scale, become zeros
+            const int c0 = hsel == 1 ? BN : 0, nc2 = (hsel >= 0 ? BN : TB) / 2;
+            for (int idx = tid; idx < TB * nc2; idx += 256) {
+                const int row = idx / nc2, c2 = idx - row * nc2;
+                *reinterpret_cast<double2*>(Aik + (size_t)row * ld + c0 + 2 * c2) = make_double2(0.0, 0.0);
+            }
+        }
     }
     double part[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][4][2];

@@ -411,3 +411,37 @@ def test_skipping_with_sub_batch_streams(monkeypatch):
     dense = _ll_with_env(monkeypatch, {"AGPN_I8_SKIP": "0"}, N, theta)
     assert np.array_equal(out, dense)
     assert st[1] < st[0]
+
+
+def test_prediction_with_and_without_zero_chunk_skipping(monkeypatch):
+    """The stacked [K ; K*] factorisation uses the same masks and bound test (K* is banded too: a grid point far from
+    every training time adds nothing).  Mean and variance agree with the dense schedule far below the 1e-9 gate, and
+    with the oracle."""
+    from artgpn_b200 import node, weight, mean
+    N, M = 1100, 5000
+    res = {}
+    for skip in ("1", "0"):
+        monkeypatch.setenv("AGPN_I8_SKIP", skip)
+        net, (t, y, sig) = _net(N, 2, 2, seed=4)
+        nodes = [node.QuasiPeriodic(18.0, 23.0, 0.8), node.SquaredExponential(30.0)]
+        ws = [weight.Constant(1.4), weight.Constant(0.8), weight.Constant(1.0), weight.Constant(1.2)]
+        ms = [mean.Linear(0.01, 0.2), mean.Constant(0.1)]
+        jit = [0.5, 0.7]
+        grid = np.linspace(t.min() - 5, t.max() + 5, M)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mu, sd, _ = net.prediction(nodes=nodes, weights=ws, means=ms, jitters=jit, time=grid, dataset=2)
+        assert net.predict_path() == 1
+        res[skip] = (mu, sd)
+        net.close()
+    monkeypatch.delenv("AGPN_I8_SKIP", raising=False)
+    mu1, sd1 = res["1"]
+    mu0, sd0 = res["0"]
+    assert np.max(np.abs(mu1 - mu0)) <= 1e-14 * np.max(np.abs(mu0))
+    assert np.max(np.abs(sd1 ** 2 - sd0 ** 2)) <= 1e-14 * np.max(sd0 ** 2)
+    idx = np.arange(0, M, 25)
+    emu, esd = oracle.prediction(t, y, sig, 2, [("QuasiPeriodic", [18.0, 23.0, 0.8]), ("SquaredExponential", [30.0])],
+                                 [("Constant", [1.4]), ("Constant", [0.8]), ("Constant", [1.0]), ("Constant", [1.2])],
+                                 [("Linear", [0.01, 0.2]), ("Constant", [0.1])], jit, grid, 2)
+    assert np.max(np.abs(mu1 - emu)) <= 1e-9 * np.max(np.abs(emu))
+    assert np.max(np.abs(sd1 ** 2 - esd ** 2)) <= 1e-9 * np.max(esd ** 2)
+    assert idx.size
