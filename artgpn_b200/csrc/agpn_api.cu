@@ -174,8 +174,11 @@ struct agpn_ctx {
     bool i8_skip = true;
     unsigned long long* d_nzmask = nullptr;     // [cap_mats][nblk][nzwords]
     int nzwords = 0;
+    bool tile_bounds = true;                    // AGPN_TILE_BOUNDS=0: the panel solve's bound test always scans the tile itself
     bool trsm_skip = true;                      // AGPN_TRSM_SKIP=0: panel solves never leave a negligible tile half out
     double* d_linvnorm = nullptr;               // [cap_mats][linv_blocks][2]
+    double* d_tmaxA = nullptr;                  // [cap_mats][nblk (nblk + 1) / 2] bound on |K| per assembled tile (fast assembly kernel)
+    unsigned long long* d_tmaxU = nullptr;      // [cap_mats][nblk][nblk] scaled maximum of the tiles the update has rewritten
     unsigned long long* d_pmask = nullptr;      // prediction: masks of the stacked factor | 2 counters | 2 inverse norms
     size_t cap_pmask = 0;
     int mask_nmat = 0;                          // matrices of the last wave that ran with masks (0: it ran dense)
@@ -308,6 +311,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_TRSM_SPLIT")) c->trsm_split = atoi(e) != 0;
     if (const char* e = getenv("AGPN_I8_SKIP")) c->i8_skip = atoi(e) != 0;
     if (const char* e = getenv("AGPN_TRSM_SKIP")) c->trsm_skip = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_TILE_BOUNDS")) c->tile_bounds = atoi(e) != 0;
     if (const char* e = getenv("AGPN_MEGA_PROF")) if (atoi(e) != 0) {
         if (cudaMalloc(&c->d_megaprof, sizeof(unsigned long long) * 16 * 2 * c->i8_clusters_max) != cudaSuccess) { cudaGetLastError(); c->d_megaprof = nullptr; }
     }
@@ -393,7 +397,7 @@ extern "C" int agpn_destroy(agpn_ctx* c) {
     cudaFree(c->d_S8); cudaFree(c->d_rscale);
     cudaFree(c->d_paug); cudaFree(c->d_ps8); cudaFree(c->d_pvec);
     cudaFree(c->d_LinvAll); cudaFree(c->d_V); cudaFree(c->d_pred); cudaFree(c->d_aug); cudaFree(c->d_augv);
-    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot); cudaFree(c->d_nzmask); cudaFree(c->d_linvnorm); cudaFree(c->d_pmask);
+    cudaFree(c->d_gather); cudaFree(c->d_gstatus); cudaFree(c->d_mega); cudaFree(c->d_megaprof); cudaFree(c->d_rslot); cudaFree(c->d_nzmask); cudaFree(c->d_linvnorm); cudaFree(c->d_pmask); cudaFree(c->d_tmaxA); cudaFree(c->d_tmaxU);
     agpn_comm_release(c);
     delete c;
     return 0;
@@ -643,13 +647,23 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
         CUDA_TRY(cudaMalloc(&c->d_info, sizeof(int) * 4 * nmat));
         cudaFree(c->d_nzmask);
         cudaFree(c->d_linvnorm);
+        cudaFree(c->d_tmaxA);
+        cudaFree(c->d_tmaxU);
         c->d_nzmask = nullptr;
         c->d_linvnorm = nullptr;
+        c->d_tmaxA = nullptr;
+        c->d_tmaxU = nullptr;
         if (c->i8_skip && c->fuse_slices && c->i8_which && c->nblk > 2) {
             const int sg = c->i8_group < 2 ? 2 : c->i8_group;
             c->nzwords = (4 * sg + 63) / 64;
             CUDA_TRY(cudaMalloc(&c->d_nzmask, sizeof(unsigned long long) * (nmat * c->nblk * c->nzwords + 2)));   // + 2 counters
-            if (c->trsm_skip) CUDA_TRY(cudaMalloc(&c->d_linvnorm, sizeof(double) * nmat * c->linv_blocks * 2));
+            if (c->trsm_skip) {
+                CUDA_TRY(cudaMalloc(&c->d_linvnorm, sizeof(double) * nmat * c->linv_blocks * 2));
+                if (c->tile_bounds) {
+                    CUDA_TRY(cudaMalloc(&c->d_tmaxA, sizeof(double) * nmat * ((size_t)c->nblk * (c->nblk + 1) / 2)));
+                    CUDA_TRY(cudaMalloc(&c->d_tmaxU, sizeof(unsigned long long) * nmat * c->nblk * c->nblk));
+                }
+            }
         }
         cudaFree(c->d_rslot);
         c->d_rslot = nullptr;
@@ -723,6 +737,8 @@ static int run_cholesky(agpn_ctx* c, CholArgs& g, cudaStream_t st, size_t* curso
     if (g.nzmask != nullptr && !(i8 != 0 && c->i8_persist && c->fuse_slices && group >= kstop)) {
         g.nzmask = nullptr;
         g.linvnorm = nullptr;
+        g.tmaxA = nullptr;
+        g.tmaxU = nullptr;
         g.nzstat = nullptr;
         c->mask_nmat = 0;
     }
@@ -834,8 +850,10 @@ static int launch_assemble(agpn_ctx* c, AsmArgs& a, int W, cudaStream_t st) {
         tiles = ((a.rows_out + ASM_TILE - 1) / ASM_TILE) * ((a.cols_out + ASM_TILE - 1) / ASM_TILE);
     }
     bool wse = false;
+    a.tmax_valid = 0;
     if (fast_assembly_ok(c, a, &wse)) {
         const dim3 grid(tiles, W);
+        a.tmax_valid = (a.tmax != nullptr && a.lower_only) ? 1 : 0;
         switch (a.nser) {
             case 1: launch_fast<1>(c, a, wse, grid, st); break;
             case 2: launch_fast<2>(c, a, wse, grid, st); break;
@@ -881,6 +899,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     }
     const int small_nb = (c->N + 15) / 16;
     const bool use_small = !c->no_small && small_nb <= SM_MAXNB;
+    bool tmax_valid = false;
     if (use_small) {
         // K0: assembly + factorisation + solve fused in one CTA's shared memory per (walker, series)
         PhaseScope ps(c, st, PH_ASM, cur);
@@ -908,7 +927,9 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         a.mat_stride = (long long)(np * np); a.ld = c->npad; a.series0 = 0; a.nser = p;
         a.lower_only = 1; a.square = 1; a.add_err = 1; a.add_jit = 1; a.pad_identity = 1;
         a.use_trig = 1; a.vec2 = 1; a.torigin = c->t0; a.kflag = d_kflag; a.exact = c->exact ? 1 : 0;
+        a.tmax = c->d_tmaxA;
         if (launch_assemble(c, a, Ww, st)) return 1;
+        tmax_valid = a.tmax_valid != 0;
     }
     CholArgs g;
     g.A = c->d_A; g.mat_stride = (long long)(np * np); g.ld = c->npad; g.nblk = c->nblk; g.nmat = nmat;
@@ -943,6 +964,11 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             // masks are rebuilt by every wave's panel solves (one group of all block columns: kc32 = 4 k + chunk)
             g.nzmask = c->d_nzmask; g.nzwords = c->nzwords;
             g.linvnorm = c->d_linvnorm;
+            if (c->d_linvnorm && c->d_tmaxU) {
+                g.tmaxU = c->d_tmaxU;
+                if (tmax_valid) g.tmaxA = c->d_tmaxA;
+                CUDA_TRY(cudaMemsetAsync(c->d_tmaxU, 0, sizeof(unsigned long long) * (size_t)nmat * c->nblk * c->nblk, st));
+            }
             g.nzstat = c->d_nzmask + (size_t)c->cap_mats * c->nblk * c->nzwords;
             c->mask_nmat = (int)nmat;
             CUDA_TRY(cudaMemsetAsync(c->d_nzmask, 0, sizeof(unsigned long long) * (size_t)nmat * c->nblk * c->nzwords, st));
@@ -982,6 +1008,8 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             if (g.rslot) gs.rslot = g.rslot + rslot_off(g.nblk, m0, 0, 0, 0);
             if (g.nzmask) gs.nzmask = g.nzmask + (size_t)m0 * g.nblk * g.nzwords;
             if (g.linvnorm) gs.linvnorm = g.linvnorm + (size_t)m0 * g.linv_blocks * 2;
+            if (g.tmaxA) gs.tmaxA = g.tmaxA + (size_t)m0 * ((size_t)g.nblk * (g.nblk + 1) / 2);
+            if (g.tmaxU) gs.tmaxU = g.tmaxU + (size_t)m0 * g.nblk * g.nblk;
             gs.nmat = m1 - m0;
             gs.mat0 = m0;
             if (g.S8) {

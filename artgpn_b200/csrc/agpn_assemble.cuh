@@ -37,6 +37,11 @@ struct AsmArgs {
     int exact;               // reference operation order, no hoisting / tables / fma (kern_value_exact)
     double torigin;          // phase origin of the tables
     int* kflag;              // [W * nser] set to 1 if a produced entry is not finite (or nullptr)
+    // assemble_fast_kernel only, lower_only grids: an upper bound on |entry| over each off-diagonal tile, from the decay of
+    // the squared-exponential factors at the tile's smallest lag -- [W * nser][tiles] (the panel solve's bound test reads
+    // this instead of the tile).  tmax_valid is set by launch_assemble when the kernel that ran has written it.
+    double* tmax = nullptr;
+    int tmax_valid = 0;
 };
 
 __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ Structure S, const AsmArgs g) {
@@ -390,6 +395,29 @@ __global__ void __launch_bounds__(256, 2) assemble_fast_kernel(const __grid_cons
     }
     __syncthreads();
 
+    if (g.tmax != nullptr && bi != bj) {                       // CTA-uniform
+        // every entry is sum_j amp_sj exp(c_sj r^2 + a_j sin^2(..)) with a_j, c_sj <= 0:  <= sum_j amp_sj exp(c_sj r_min^2)
+        __shared__ double s_mm[8][2];
+        const double v = (tid < ASM_TILE) ? s_ta[tid] : s_tb[tid - ASM_TILE];
+        double lo = v, hi = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((tid & 31) == 0) { s_mm[tid >> 5][0] = lo; s_mm[tid >> 5][1] = hi; }
+        __syncthreads();
+        if (tid < P) {
+            const double lo_a = fmin(fmin(s_mm[0][0], s_mm[1][0]), fmin(s_mm[2][0], s_mm[3][0]));
+            const double hi_a = fmax(fmax(s_mm[0][1], s_mm[1][1]), fmax(s_mm[2][1], s_mm[3][1]));
+            const double lo_b = fmin(fmin(s_mm[4][0], s_mm[5][0]), fmin(s_mm[6][0], s_mm[7][0]));
+            const double hi_b = fmax(fmax(s_mm[4][1], s_mm[5][1]), fmax(s_mm[6][1], s_mm[7][1]));
+            const double rmin = fmax(0.0, fmax(lo_a - hi_b, lo_b - hi_a));
+            double bound = 0.0;
+            for (int j = 0; j < q; ++j) bound += fabs(s_amp[tid][j]) * exp(s_cs[tid][j] * rmin * rmin);
+            g.tmax[((size_t)w * P + tid) * gridDim.x + t] = bound * 1.000001;       // NaN parameters give NaN: "unknown"
+        }
+    }
     double chk[P];
 #pragma unroll
     for (int s = 0; s < P; ++s) chk[s] = 0.0;

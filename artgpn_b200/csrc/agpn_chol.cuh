@@ -82,6 +82,11 @@ struct CholArgs {
     // below 2^-40 of one digit unit -- below 2^-96 of its row scale, 2^-43 of an ulp of anything it could be added to.
     // nullptr: never.
     double* linvnorm = nullptr;
+    // what the bound test knows about a tile without reading it: tmaxA[mat][lower tile index] bounds |K| of the assembled
+    // tile (assemble_fast_kernel), tmaxU[mat][ti][k] holds max_i |C_ij| Q / r_i (bits of a non-negative double, 0 = not
+    // recorded) of a tile the persistent update has just rewritten.  Either nullptr: the test scans the tile itself.
+    const double* tmaxA = nullptr;
+    unsigned long long* tmaxU = nullptr;
     unsigned long long* nzstat = nullptr;       // or nullptr: tile halves left out, [0] left (K = 64) and [1] right (K = 128) halves (agpn_skip_stats)
 };
 #define TRSM_SKIP_BOUND 9.094947017729282e-13      /* 2^-40 */
@@ -422,6 +427,25 @@ __global__ void __launch_bounds__(256, 2) syrk_kernel(CholArgs g, int kfirst, in
     }
 }
 
+// K steps (32-column chunks ks < nks) of tile (ti, tj) in which BOTH operands hold a non-zero digit, 64 per word
+// (CholArgs::nzmask; without masks every step is active)
+__device__ __forceinline__ unsigned long long i8_active_word(const CholArgs& g, int mat, int ti, int tj, int word, int nks) {
+    const int left = nks - word * 64;
+    if (left <= 0) return 0ull;
+    unsigned long long a = ~0ull;
+    if (g.nzmask != nullptr)
+        a = g.nzmask[((size_t)mat * g.nblk + ti) * g.nzwords + word] & g.nzmask[((size_t)mat * g.nblk + tj) * g.nzwords + word];
+    if (left < 64) a &= (1ull << left) - 1ull;
+    return a;
+}
+__device__ __forceinline__ bool i8_any_active(const CholArgs& g, int mat, int ti, int tj, int nks) {
+    if (g.nzmask == nullptr) return nks > 0;
+    for (int wd = 0; wd * 64 < nks; ++wd)
+        if (i8_active_word(g, mat, ti, tj, wd, nks)) return true;
+    return false;
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // panel solve: A_ik <- A_ik * Linv_kk^T (i > k), and rhs_i -= L_ik z_k
 // grid.x = nblk-k-1, grid.y = nmat.  Two passes per CTA over the two 64-column halves; the right
@@ -512,10 +536,25 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
         // bound the half (split) or the tile before touching the tensor pipe
         const double* ln = g.linvnorm + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * 2;
         const double lnorm = hsel >= 0 ? ln[hsel] : fmax(ln[0], ln[1]);
-        // warp w scans rows 16 w .. 16 w + 15, a row's columns spread over the lanes (coalesced), eight rows in flight
-        const int nld = hsel == 0 ? 1 : 2;                      // double2 loads per lane and row: 64 or 128 input columns
         const double thr = TRSM_SKIP_BOUND / lnorm;              // lnorm inf / NaN: nothing passes
         int bad = 0;
+        // without reading the tile: the update has just rewritten it and recorded max |C_ij| Q / r_i, or no K step of it was
+        // active (same mask test as the update kernel) and it still holds the assembled entries, bounded by tmaxA
+        double known = -1.0;                                    // bound on |C_ij| (x Q / r_i if `scaled`), < 0: unknown
+        bool scaled = false;
+        if (k > k0 && i8_any_active(g, mat, ti, k, 4 * (k - k0))) {
+            if (g.tmaxU != nullptr) {
+                const unsigned long long b = g.tmaxU[((size_t)mat * g.nblk + ti) * g.nblk + k];
+                if (b != 0ull) { known = __longlong_as_double((long long)b); scaled = true; }
+            }
+        } else if (g.tmaxA != nullptr && k0 == 0) {
+            known = g.tmaxA[(size_t)mat * ((size_t)g.nblk * (g.nblk + 1) / 2) + (size_t)ti * (ti + 1) / 2 + k];
+        }
+        if (known >= 0.0) {                                      // false for NaN
+            if (tid < TB) bad = !(known * (scaled ? 1.0 : qs[tid]) < thr);
+        } else {
+        // warp w scans rows 16 w .. 16 w + 15, a row's columns spread over the lanes (coalesced), eight rows in flight
+        const int nld = hsel == 0 ? 1 : 2;                      // double2 loads per lane and row: 64 or 128 input columns
 #pragma unroll
         for (int r8 = 0; r8 < 2; ++r8) {
             double2 v[8][2];
@@ -531,6 +570,7 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
                 const double m = (fabs(v[r][0].x) + fabs(v[r][0].y)) + (fabs(v[r][1].x) + fabs(v[r][1].y));
                 bad |= !(m * qs[warp * 16 + r8 * 8 + r] < thr);   // NaN / inf count as "solve it"
             }
+        }
         }
         if constexpr (!G) {
             skip = __syncthreads_or(bad) == 0;

@@ -418,24 +418,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// K steps (32-column chunks ks < nks) of tile (ti, tj) in which BOTH operands hold a non-zero digit, 64 per word
-// (CholArgs::nzmask; without masks every step is active)
-__device__ __forceinline__ unsigned long long i8_active_word(const CholArgs& g, int mat, int ti, int tj, int word, int nks) {
-    const int left = nks - word * 64;
-    if (left <= 0) return 0ull;
-    unsigned long long a = ~0ull;
-    if (g.nzmask != nullptr)
-        a = g.nzmask[((size_t)mat * g.nblk + ti) * g.nzwords + word] & g.nzmask[((size_t)mat * g.nblk + tj) * g.nzwords + word];
-    if (left < 64) a &= (1ull << left) - 1ull;
-    return a;
-}
-__device__ __forceinline__ bool i8_any_active(const CholArgs& g, int mat, int ti, int tj, int nks) {
-    if (g.nzmask == nullptr) return nks > 0;
-    for (int wd = 0; wd * 64 < nks; ++wd)
-        if (i8_active_word(g, mat, ti, tj, wd, nks)) return true;
-    return false;
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_PTHREADS, 1)
 syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles, int total, int bi0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -595,6 +577,9 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
             if (et == 0) mbar_expect_tx(cfull, (half_tile ? TB / 2 : TB) * BN * 8);
             if (!skip) bulk_g2s(crow, Crow, CW * 8, cfull);
             const double ei = esc[ti * TB + row];
+            const bool record = narrow && g.tmaxU != nullptr;       // the panel solve's bound test reads the tile's maximum
+            const double qrow = record ? g.rscale[(size_t)mat * 2 * n + ti * TB + row] : 0.0;     // Q / r_i
+            double rmax = 0.0;
             named_bar_sync(1, 32 * I8_EPW);                         // ecol[eb] visible to all epilogue warps
             mbar_wait(done, tile & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -627,11 +612,23 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
                         cc.x -= r2[0];
                         cc.y -= r2[1];
                         *reinterpret_cast<double2*>(cgen + c8 * 8 + j2) = cc;
+                        const double m2 = fabs(cc.x) + fabs(cc.y);  // bounds the larger one and keeps a NaN
+                        rmax = (m2 > rmax || m2 != m2) ? m2 : rmax;
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                 bulk_s2g(Crow, crow, CW * 8);
                 asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                if (record) {
+                    double v = rmax * qrow;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double u = __shfl_xor_sync(0xffffffffu, v, o);
+                        v = (u > v || u != u) ? u : v;
+                    }
+                    // non-negative doubles (and NaN above them all) order like their bit patterns
+                    if (lane == 0) atomicMax(g.tmaxU + ((size_t)mat * g.nblk + ti) * g.nblk + tj, (unsigned long long)__double_as_longlong(v));
+                }
                 asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");       // the row buffer is free for the next tile's load
             } else {
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
