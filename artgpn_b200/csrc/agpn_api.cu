@@ -185,6 +185,7 @@ struct agpn_ctx {
     int wave_nmat = 0;                          // matrices of the last wave
     // panel solves with one CTA per 64-column half of a tile (AGPN_TRSM_SPLIT=0: one CTA per tile)
     bool trsm_split = true;
+    bool trsm_split_fixed = false;  // AGPN_TRSM_SPLIT given: for every batch size (default: fewer than 144 matrices only)
     double* d_rslot = nullptr;     // [cap_mats][nblk][2][2][128] parked forward-solve sums of the split panel solves
     // persistent tile-task kernel (agpn_mega.cuh): one launch per wave instead of the per-column chain; opt-in
     bool use_mega = false;         // AGPN_MEGA=1 enables it (measured: 23.9 vs 21.1 ms at 128 walkers, 3.66 vs 3.24 ms at 16)
@@ -308,7 +309,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_I8_PERSIST")) c->i8_persist = atoi(e) != 0;
     if (const char* e = getenv("AGPN_I8_BALANCE")) c->i8_balance = atoi(e) != 0;
     if (const char* e = getenv("AGPN_MEGA")) c->use_mega = atoi(e) != 0;
-    if (const char* e = getenv("AGPN_TRSM_SPLIT")) c->trsm_split = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_TRSM_SPLIT")) { c->trsm_split = atoi(e) != 0; c->trsm_split_fixed = true; }
     if (const char* e = getenv("AGPN_I8_SKIP")) c->i8_skip = atoi(e) != 0;
     if (const char* e = getenv("AGPN_TRSM_SKIP")) c->trsm_skip = atoi(e) != 0;
     if (const char* e = getenv("AGPN_TILE_BOUNDS")) c->tile_bounds = atoi(e) != 0;
@@ -957,7 +958,10 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         // split panel solves: on the pure INT8 likelihood path every panel solve of the wave leaves its FP64 panel unstored,
         // so every launch can be split (the task kernel keeps one CTA group per tile)
         const bool mega_wave = mega_eligible(c) && c->d_mega && !c->profiling && !c->timeline;
-        if (c->trsm_split && c->d_rslot && c->i8_which == 3 && c->fuse_slices && c->i8_group >= c->nblk && !mega_wave) g.rslot = c->d_rslot;
+        // (measured with the banded schedule, 3 x 2048: split wins below ~ 40 walkers -- 16 walkers 2.11 vs 2.17 ms -- and loses
+        // above, where half of its CTAs only find out that there is nothing to do: 128 walkers 11.29 vs 11.00 ms)
+        if (c->trsm_split && (c->trsm_split_fixed || nmat < 144) && c->d_rslot && c->i8_which == 3 && c->fuse_slices &&
+            c->i8_group >= c->nblk && !mega_wave) g.rslot = c->d_rslot;
         c->mask_nmat = 0;
         c->wave_nmat = (int)nmat;
         if (c->d_nzmask && c->i8_group >= c->nblk && !mega_wave) {
@@ -1019,7 +1023,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
             CUDA_TRY(cudaStreamWaitEvent(c->sub[si], c->ev_fork, 0));
             const LookAhead la = {c->side[si], c->ev_la[si][0], c->ev_la[si][1]};
             // measured (3 x 2048): +4 % at 8 walkers, nothing at 16, -2 % at 128; 3 x 8192, 4 walkers: +2 %
-            const bool use_la = c->lookahead && gs.S8 && (c->lookahead_forced || nmat <= 24);
+            const bool use_la = c->lookahead && gs.S8 && (c->lookahead_forced || nmat <= 48);
             if (run_cholesky(c, gs, c->sub[si], c->timeline ? &cur : nullptr, -1, false, use_la ? &la : nullptr)) return 1;
             CUDA_TRY(cudaEventRecord(c->ev_join[si], c->sub[si]));
             CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join[si], 0));
