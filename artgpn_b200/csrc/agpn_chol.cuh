@@ -531,13 +531,14 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
         }
     }
     grp_sync<G>();
-    bool skip = false;
+    // skip_h[h]: the 64-column half h of the tile is left out.  One CTA per half (hsel) decides for its half, a CTA that owns
+    // the whole tile for both -- with the same bounds and the same arithmetic, so the results do not depend on the launch mode
+    bool skip_h[2] = {false, false};
     if (g.linvnorm != nullptr && g.nzmask != nullptr && (flags & 1) && !refine) {
-        // bound the half (split) or the tile before touching the tensor pipe
+        // bound the half before touching the tensor pipe: |X_ic| <= max_j |C_ij| * ||rows of Linv of this half||_inf
         const double* ln = g.linvnorm + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * 2;
-        const double lnorm = hsel >= 0 ? ln[hsel] : fmax(ln[0], ln[1]);
-        const double thr = TRSM_SKIP_BOUND / lnorm;              // lnorm inf / NaN: nothing passes
-        int bad = 0;
+        const double thr0 = TRSM_SKIP_BOUND / ln[0], thr1 = TRSM_SKIP_BOUND / ln[1];     // norm inf / NaN: nothing passes
+        int bad0 = 0, bad1 = 0;
         // without reading the tile: the update has just rewritten it and recorded max |C_ij| Q / r_i, or no K step of it was
         // active (same mask test as the update kernel) and it still holds the assembled entries, bounded by tmaxA
         double known = -1.0;                                    // bound on |C_ij| (x Q / r_i if `scaled`), < 0: unknown
@@ -551,54 +552,62 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
             known = g.tmaxA[(size_t)mat * ((size_t)g.nblk * (g.nblk + 1) / 2) + (size_t)ti * (ti + 1) / 2 + k];
         }
         if (known >= 0.0) {                                      // false for NaN
-            if (tid < TB) bad = !(known * (scaled ? 1.0 : qs[tid]) < thr);
+            if (tid < TB) {
+                const double v = known * (scaled ? 1.0 : qs[tid]);
+                bad0 = !(v < thr0);
+                bad1 = !(v < thr1);
+            }
         } else {
-        // warp w scans rows 16 w .. 16 w + 15, a row's columns spread over the lanes (coalesced), eight rows in flight
-        const int nld = hsel == 0 ? 1 : 2;                      // double2 loads per lane and row: 64 or 128 input columns
+            // warp w scans rows 16 w .. 16 w + 15, a row's columns spread over the lanes (coalesced), eight rows in flight;
+            // the left half depends on input columns 0 .. 63 only, the right half on all 128
+            const bool want_right = hsel != 0;
 #pragma unroll
-        for (int r8 = 0; r8 < 2; ++r8) {
-            double2 v[8][2];
+            for (int r8 = 0; r8 < 2; ++r8) {
+                double2 v[8][2];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const double* src = Aik + (size_t)(warp * 16 + r8 * 8 + r) * ld;
-                v[r][0] = *reinterpret_cast<const double2*>(src + 2 * lane);
-                v[r][1] = nld == 2 ? *reinterpret_cast<const double2*>(src + 64 + 2 * lane) : make_double2(0.0, 0.0);
-            }
+                for (int r = 0; r < 8; ++r) {
+                    const double* src = Aik + (size_t)(warp * 16 + r8 * 8 + r) * ld;
+                    v[r][0] = *reinterpret_cast<const double2*>(src + 2 * lane);
+                    v[r][1] = want_right ? *reinterpret_cast<const double2*>(src + 64 + 2 * lane) : make_double2(0.0, 0.0);
+                }
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                // the sum bounds the maximum and, unlike fmax, keeps a NaN
-                const double m = (fabs(v[r][0].x) + fabs(v[r][0].y)) + (fabs(v[r][1].x) + fabs(v[r][1].y));
-                bad |= !(m * qs[warp * 16 + r8 * 8 + r] < thr);   // NaN / inf count as "solve it"
+                for (int r = 0; r < 8; ++r) {
+                    // the sums bound the maxima and, unlike fmax, keep a NaN
+                    const double q = qs[warp * 16 + r8 * 8 + r];
+                    const double ml = fabs(v[r][0].x) + fabs(v[r][0].y);
+                    const double ma = ml + (fabs(v[r][1].x) + fabs(v[r][1].y));
+                    bad0 |= !(ml * q < thr0);                    // NaN / inf count as "solve it"
+                    bad1 |= !(ma * q < thr1);
+                }
             }
         }
-        }
-        if constexpr (!G) {
-            skip = __syncthreads_or(bad) == 0;
-        } else {
-            if (tid == 0) s_nz[0] = 0;
-            grp_sync<G>();
-            if (bad) s_nz[0] = 1;
-            grp_sync<G>();
-            skip = s_nz[0] == 0;
-            grp_sync<G>();
-        }
-        if (skip && tid == 0 && g.nzstat != nullptr) atomicAdd(g.nzstat + (hsel == 0 ? 0 : 1), hsel >= 0 ? 1ull : 2ull);
-        if (skip && !(flags & 2)) {
-            // the FP64 panel is kept (prediction reads V back): the tile's entries, below 2^-96 of their row scale, become zeros
-            const int c0 = hsel == 1 ? BN : 0, nc2 = (hsel >= 0 ? BN : TB) / 2;
-            for (int idx = tid; idx < TB * nc2; idx += 256) {
-                const int row = idx / nc2, c2 = idx - row * nc2;
-                *reinterpret_cast<double2*>(Aik + (size_t)row * ld + c0 + 2 * c2) = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (hsel >= 0 && h != hsel) continue;
+            const int bad = h ? bad1 : bad0;
+            if constexpr (!G) {
+                skip_h[h] = __syncthreads_or(bad) == 0;
+            } else {
+                if (tid == 0) s_nz[0] = 0;
+                grp_sync<G>();
+                if (bad) s_nz[0] = 1;
+                grp_sync<G>();
+                skip_h[h] = s_nz[0] == 0;
+                grp_sync<G>();
             }
+            if (skip_h[h] && tid == 0 && g.nzstat != nullptr) atomicAdd(g.nzstat + h, 1ull);
         }
     }
+    // forward-solve sums: a CTA that owns both halves keeps them apart and adds them like the two CTAs of a split solve do
+    const bool two_sums = rhs != nullptr && !refine && hsel < 0;
+    double hsum[2] = {0.0, 0.0};
     double part[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][4][2];
-    if (!skip)
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         const int h = 1 - pass;
         if (hsel >= 0 && h != hsel) continue;
+        if (skip_h[h]) continue;                                 // CTA-uniform
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -676,8 +685,34 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
             }
             grp_sync<G>();                                       // the next pass refills the pipeline buffers
         }
+        if (two_sums) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                double s = part[mi];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if ((lane & 3) == 0) red[wn][wm * 32 + mi * 8 + (lane >> 2)] = s;
+                part[mi] = 0.0;
+            }
+            grp_sync<G>();
+            if (tid < TB) hsum[h] = red[0][tid] + red[1][tid];
+            grp_sync<G>();
+        }
     }
-    if (rhs != nullptr) {
+    if (!(flags & 2)) {
+        // the FP64 panel is kept (prediction reads V back): a half that was left out -- entries below 2^-96 of their row
+        // scale -- becomes zeros, after the other half's solve has read its input columns
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (skip_h[h])
+                for (int idx = tid; idx < TB * (BN / 2); idx += 256) {
+                    const int row = idx / (BN / 2), c2 = idx - row * (BN / 2);
+                    *reinterpret_cast<double2*>(Aik + (size_t)row * ld + h * BN + 2 * c2) = make_double2(0.0, 0.0);
+                }
+    }
+    if (two_sums) {
+        if (tid < TB) rhs[(size_t)ti * TB + tid] -= hsum[0] + hsum[1];
+    } else if (rhs != nullptr) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             double s = part[mi];

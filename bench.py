@@ -547,7 +547,7 @@ def main():
         syrk_tf = W_local * p * syrk_tiles * 2.0 * 128 ** 3 / (phase[4] * 1e-3) / 1e12 if phase[4] > 0 else None
         asm_bytes = W_local * 4.0 * p * N * (N + 1)               # triangle-only store: B_tri = 4 p N (N+1)
         asm_gbs = asm_bytes / (phase[1] * 1e-3) / 1e9 if phase[1] > 0 else None
-        chol_traffic = asm_traffic = syrk_traffic = None          # DRAM bytes from the committed ncu pass
+        chol_traffic = asm_traffic = syrk_traffic = trsm_traffic = None          # DRAM bytes from the committed ncu pass
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tr = json.load(f)
@@ -555,6 +555,7 @@ def main():
                 chol_traffic = tr["cholesky_dram_bytes_per_step"] * W_local / tr["walkers"]
                 asm_traffic = tr["assembly_dram_bytes_per_launch"] * W_local / tr["walkers"]
                 syrk_traffic = tr["syrk_dram_bytes_per_step"] * W_local / tr["walkers"]
+                trsm_traffic = tr["trsm_dram_bytes_per_step"] * W_local / tr["walkers"]
         except Exception:
             pass
         dmma_peak = float(peak_tf[0])
@@ -604,7 +605,8 @@ def main():
                 "peak_source": "DMMA.8x8x4 issue peak measured in this run (agpn_dmma_peak); MEASURED_PEAKS.json has no FP64 figure",
                 "flops_per_step": trsm_flops, "tile_halves": skip[2] * scale, "tile_halves_left_out": skip[3] * scale,
                 "ms": float(phase[3]), "launches": int(nl[3]), "share_of_step_ms": float(phase[3] / max(step_prof_ms, 1e-9)),
-                "traffic": None,
+                "traffic": trsm_traffic,
+                "traffic_note": "DRAM bytes of all trsm_kernel launches of one step, ncu pass in profiles/ (scaled by walkers)",
                 "note": "EXECUTED GEMM flops of the halves that were solved; halves whose entries are bounded below 2^-96 of "
                         "their row scale are left out after a read-only bound pass (AGPN_TRSM_SKIP=0: none)"}
             # `roofline` = the kernel with the largest share of the step

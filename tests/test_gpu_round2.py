@@ -445,3 +445,17 @@ def test_prediction_with_and_without_zero_chunk_skipping(monkeypatch):
     assert np.max(np.abs(mu1 - emu)) <= 1e-9 * np.max(np.abs(emu))
     assert np.max(np.abs(sd1 ** 2 - esd ** 2)) <= 1e-9 * np.max(esd ** 2)
     assert idx.size
+
+
+def test_results_do_not_depend_on_the_batch_size_or_launch_mode():
+    """Small batches split every panel solve over two CTAs, use look-ahead and six sub-batch streams; large ones one CTA per
+    tile and three or four streams.  A walker's log-likelihood has the same bits in all of them."""
+    from artgpn_b200 import synth, node, weight, mean
+    N = 1100
+    theta = synth.make_walkers(50, p=3, q=2, seed=5)
+    net, _ = _net(N, 3, 2)
+    net.set_structure(*synth.objects_from_row(node, weight, mean, theta[0], 3, 2)[:3])
+    big = net.log_likelihood_batch(theta)              # 150 matrices
+    for W in (1, 5, 16, 33):
+        assert np.array_equal(net.log_likelihood_batch(theta[:W]), big[:W]), W
+    net.close()
