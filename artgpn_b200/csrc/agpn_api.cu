@@ -174,6 +174,7 @@ struct agpn_ctx {
     bool i8_skip = true;
     unsigned long long* d_nzmask = nullptr;     // [cap_mats][nblk][nzwords]
     int nzwords = 0;
+    int tile_order = -1;                        // AGPN_TILE_ORDER (CholArgs::tile_order); -1: by size
     bool tile_bounds = true;                    // AGPN_TILE_BOUNDS=0: the panel solve's bound test always scans the tile itself
     bool trsm_skip = true;                      // AGPN_TRSM_SKIP=0: panel solves never leave a negligible tile half out
     double* d_linvnorm = nullptr;               // [cap_mats][linv_blocks][2]
@@ -313,6 +314,7 @@ extern "C" int agpn_create(agpn_ctx** out, int device, int N, int p, int q, cons
     if (const char* e = getenv("AGPN_I8_SKIP")) c->i8_skip = atoi(e) != 0;
     if (const char* e = getenv("AGPN_TRSM_SKIP")) c->trsm_skip = atoi(e) != 0;
     if (const char* e = getenv("AGPN_TILE_BOUNDS")) c->tile_bounds = atoi(e) != 0;
+    if (const char* e = getenv("AGPN_TILE_ORDER")) c->tile_order = atoi(e);
     if (const char* e = getenv("AGPN_MEGA_PROF")) if (atoi(e) != 0) {
         if (cudaMalloc(&c->d_megaprof, sizeof(unsigned long long) * 16 * 2 * c->i8_clusters_max) != cudaSuccess) { cudaGetLastError(); c->d_megaprof = nullptr; }
     }
@@ -967,6 +969,9 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         if (c->d_nzmask && c->i8_group >= c->nblk && !mega_wave) {
             // masks are rebuilt by every wave's panel solves (one group of all block columns: kc32 = 4 k + chunk)
             g.nzmask = c->d_nzmask; g.nzwords = c->nzwords;
+            // long block rows with few live tiles (3 x 8192: update 14.66 -> 13.56 ms) like the matrix-fastest walk, many short ones
+            // do not (3 x 2048, 128 walkers: 3.63 -> 3.74 ms: the tiles of one matrix share their B planes in L2)
+            g.tile_order = c->tile_order >= 0 ? c->tile_order : (c->nblk >= 32 ? 1 : 0);
             g.linvnorm = c->d_linvnorm;
             if (c->d_linvnorm && c->d_tmaxU) {
                 g.tmaxU = c->d_tmaxU;

@@ -460,8 +460,17 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
 
     // tile w -> (matrix, block row ti, block column tj)
     auto decode = [&](int w, int& mat, int& ti, int& tj, bool& diag) {
-        mat = w / ntiles;
-        const int t = w - mat * ntiles;
+        int t;
+        if (g.tile_order == 1 && narrow) {
+            // matrix index fastest: the tiles next to the diagonal (the ones with active K steps in a banded factor) of all
+            // matrices come first and spread evenly over the clusters, the far tiles that are only looked at come last
+            const int nm = total / ntiles;
+            t = w / nm;
+            mat = w - t * nm;
+        } else {
+            mat = w / ntiles;
+            t = w - mat * ntiles;
+        }
         int bi, bj;
         if (narrow) {
             bi = t + bi0;                                           // bi0 = 1: the tiles below the diagonal tile only
@@ -620,14 +629,13 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
                 bulk_s2g(Crow, crow, CW * 8);
                 asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                 if (record) {
-                    double v = rmax * qrow;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double u = __shfl_xor_sync(0xffffffffu, v, o);
-                        v = (u > v || u != u) ? u : v;
+                    // an upper bound is all the reader needs: round up to a float, whose bit patterns order like the values for
+                    // non-negative numbers (NaN above them all) -- one redux.sync per warp, widened back to a double's bits
+                    const unsigned fb = __reduce_max_sync(0xffffffffu, __float_as_uint(__double2float_ru(rmax * qrow)));
+                    if (lane == 0) {
+                        const double v = (double)__uint_as_float(fb);
+                        atomicMax(g.tmaxU + ((size_t)mat * g.nblk + ti) * g.nblk + tj, (unsigned long long)__double_as_longlong(v));
                     }
-                    // non-negative doubles (and NaN above them all) order like their bit patterns
-                    if (lane == 0) atomicMax(g.tmaxU + ((size_t)mat * g.nblk + ti) * g.nblk + tj, (unsigned long long)__double_as_longlong(v));
                 }
                 asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");       // the row buffer is free for the next tile's load
             } else {
