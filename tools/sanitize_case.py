@@ -20,6 +20,13 @@ def run(N, W, wk, q=2):
 variant = os.environ.get("AGPN_SYRK", "cpasync")
 net, o = run(300, 3, "Constant")                   # tiled path, fast assembly, 3 block columns
 net, o = run(300, 2, "SquaredExponential")         # fast assembly with SE weights
+net, o = run(1400, 2, "Constant")                  # 11 block columns: banded schedule (zero-chunk masks, panel tiles left out)
+st = net.skip_stats()
+assert st[1] < st[0] and st[3] > 0, st
+ts = np.linspace(56990, 58420, 1500)
+with contextlib.redirect_stdout(io.StringIO()):
+    mu, sd, _ = net.prediction(nodes=o[0], weights=o[1], means=o[2], jitters=o[3], time=ts, dataset=1)   # stacked, masks
+assert np.all(np.isfinite(mu)) and np.all(np.isfinite(sd))
 net, o = run(50, 3, "Constant")                    # K0 fused kernel
 net.set_exact(True)
 net.log_likelihood(*o)                             # exact evaluation mode
