@@ -641,6 +641,13 @@ def main():
                                           "factorisation kernels; a fraction above 1.0 means faster than the FP64 tensor "
                                           "instruction can go: the trailing update runs FP64-equivalent on the INT8 tensor path"},
             "update_path": {0: "dmma", 1: "i8 narrow", 2: "i8 wide", 3: "i8"}.get(update_path, str(update_path)),
+            "banded_schedule": {
+                "what": "work that adds nothing is not executed: K steps of the INT8-sliced update whose digit chunks are all zero "
+                        "(exact), panel-solve tile halves bounded below 2^-96 of their row scale; AGPN_I8_SKIP=0 = dense schedule",
+                "executed_k_step_fraction": (skip[1] / skip[0]) if skip[0] > 0 else 1.0,
+                "panel_halves_left_out_fraction": (skip[3] / skip[2]) if skip[2] > 0 else 0.0,
+                "bit_identical_to_dense_schedule": (extra_out.get("dense_schedule") or {}).get("bit_identical_to_the_default_schedule"),
+                "dense_schedule_ms_per_step": (extra_out.get("dense_schedule") or {}).get("ms_per_step")},
             "roofline_assembly": {"bound": "hbm", "kernel": "assemble_fast_kernel (lower block triangle only; generic assemble_kernel for other kernel classes)",
                                   "achieved": asm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                   "frac": (asm_gbs / peaks.get("hbm_gbs")) if asm_gbs else None, "peak_source": peak_src,
