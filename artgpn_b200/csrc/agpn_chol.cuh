@@ -87,7 +87,7 @@ struct CholArgs {
     // recorded) of a tile the persistent update has just rewritten.  Either nullptr: the test scans the tile itself.
     const double* tmaxA = nullptr;
     unsigned long long* tmaxU = nullptr;
-    int tile_order = 0;                         // persistent update, narrow launches: 0 = tile index fastest, 1 = matrix index fastest
+    int tile_order = 0;                         // persistent update: 0 = tile index fastest, 1 = matrix index fastest (narrow launches), 2 = 0 with a skewed round-robin
     unsigned long long* nzstat = nullptr;       // or nullptr: tile halves left out, [0] left (K = 64) and [1] right (K = 128) halves (agpn_skip_stats)
 };
 #define TRSM_SKIP_BOUND 9.094947017729282e-13      /* 2^-40 */

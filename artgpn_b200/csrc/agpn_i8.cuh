@@ -458,6 +458,10 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
     const unsigned tmem = tmem_base_s;
     const int nks = depth * (TB / I8_KB);
 
+    // Round r of the walk hands tile r * ncl + c' to cluster (c' + r) mod ncl (g.tile_order == 2): with the plain c' = cluster
+    // assignment a cluster only ever sees the tile rows t = (cluster + 74 r) mod ntiles -- half of them when ntiles is even -- and the
+    // clusters that keep drawing the tiles next to the diagonal finish last; the skew makes every cluster cycle through all rows
+    const bool skew = g.tile_order == 2;
     // tile w -> (matrix, block row ti, block column tj)
     auto decode = [&](int w, int& mat, int& ti, int& tj, bool& diag) {
         int t;
@@ -490,7 +494,9 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
         // ---------------- producer: runs ahead across tile boundaries ----------------
         if (lane == 0) {
             unsigned it = 0;                                        // K steps issued so far (all tiles)
-            for (int w = cl; w < total; w += ncl) {
+            for (int rnd = 0; rnd * ncl < total; ++rnd) {
+                const int w = rnd * ncl + (skew ? (cl + ncl - rnd % ncl) % ncl : cl);
+                if (w >= total) continue;
                 int mat, ti, tj;
                 bool diag;
                 decode(w, mat, ti, tj, diag);
@@ -520,7 +526,9 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
         if (lane == 0) {
             const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TB >> 4) << 24);
             unsigned it = 0, tile = 0;
-            for (int w = cl; w < total; w += ncl) {
+            for (int rnd = 0; rnd * ncl < total; ++rnd) {
+                const int w = rnd * ncl + (skew ? (cl + ncl - rnd % ncl) % ncl : cl);
+                if (w >= total) continue;
                 int mat, ti, tj;
                 bool diag;
                 decode(w, mat, ti, tj, diag);
@@ -572,7 +580,9 @@ syrk_i8_persistent_kernel(CholArgs g, int depth, int j0, int narrow, int ntiles,
         double* cgen = reinterpret_cast<double*>(smem_raw + (crow - sraw));
         const unsigned tlane = tmem + ((unsigned)(q * 32) << 16);
         unsigned tile = 0;
-        for (int w = cl; w < total; w += ncl) {
+        for (int rnd = 0; rnd * ncl < total; ++rnd) {
+            const int w = rnd * ncl + (skew ? (cl + ncl - rnd % ncl) % ncl : cl);
+            if (w >= total) continue;
             int mat, ti, tj;
             bool diag;
             decode(w, mat, ti, tj, diag);
