@@ -218,6 +218,9 @@ __device__ __forceinline__ void gemm_load_stage(double* stage, const double* __r
     }
 }
 
+// NI0: first of the warp's four 8-column groups that takes part (2: the triangular operand's rows of groups 0 and 1 are zero
+// in this k-chunk)
+template <int NI0 = 0>
 __device__ __forceinline__ void gemm_compute_stage(const double* stage, double (&acc)[4][4][2], int wm, int wn, int lane) {
     const double* As = stage;
     const double* Bs = stage + TB * GEMM_KC;
@@ -230,11 +233,11 @@ __device__ __forceinline__ void gemm_compute_stage(const double* stage, double (
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = As[swz(wm * 32 + mi * 8 + r, k)];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[swz(wn * 32 + ni * 8 + r, k)];
+        for (int ni = NI0; ni < 4; ++ni) b[ni] = Bs[swz(wn * 32 + ni * 8 + r, k)];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            for (int ni = NI0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
 }
 
@@ -318,11 +321,13 @@ __device__ __forceinline__ void gemm_nt_prologue(const GemmPipe& p, const double
 }
 
 // kc_limit: this warp's operand columns are exactly zero from k-chunk kc_limit on (triangular B): it skips the tensor
-// work of those chunks but still takes part in the loads and the barriers.
+// work of those chunks but still takes part in the loads and the barriers.  tri: B is lower triangular with its diagonal
+// running through the warp's last two chunks (16 columns each against the warp's 32 rows of B): in the last one the first two
+// 8-row groups of B are zero as well.
 template <bool G = false>
 __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __restrict__ Ag, int lda,
                                                  const double* __restrict__ Bg, int ldb, int K, double (&acc)[4][4][2],
-                                                 double* smem, bool active = true, int kc_limit = 1 << 30) {
+                                                 double* smem, bool active = true, int kc_limit = 1 << 30, bool tri = false) {
     const int tid = grp_tid<G>();
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -341,7 +346,10 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __re
         if (lane == 0) mbar_arrive(p.empty + 8 * s);
 #else
         mbar_wait(p.full + 8 * s, (n / GEMM_STAGES) & 1);
-        if (active && kc < kc_limit) gemm_compute_stage(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+        if (active && kc < kc_limit) {
+            if (tri && kc == kc_limit - 1) gemm_compute_stage<2>(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+            else gemm_compute_stage(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(p.empty + 8 * s);
         const int nxt = kc + GEMM_STAGES - 1;
@@ -354,9 +362,9 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __re
 template <bool G = false>
 __device__ __forceinline__ void gemm_nt_tile(GemmPipe& p, const double* __restrict__ Ag, int lda, const double* __restrict__ Bg,
                                              int ldb, int K, double (&acc)[4][4][2], double* smem, bool active = true,
-                                             int kc_limit = 1 << 30) {
+                                             int kc_limit = 1 << 30, bool tri = false) {
     gemm_nt_prologue<G>(p, Ag, lda, Bg, ldb, K, smem);
-    gemm_nt_mainloop<G>(p, Ag, lda, Bg, ldb, K, acc, smem, active, kc_limit);
+    gemm_nt_mainloop<G>(p, Ag, lda, Bg, ldb, K, acc, smem, active, kc_limit, tri);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -629,7 +637,7 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
                 }
         } else
         gemm_nt_tile<G>(pipe, Aik, ld, Linv + (size_t)h * BN * TB, TB, (h + 1) * BN, acc, smem, true,
-                     (h * BN + wn * 32 + 32) / GEMM_KC);
+                     (h * BN + wn * 32 + 32) / GEMM_KC, GEMM_KC == 16);
         // every load of this GEMM (by any thread) has completed: the in-place store is safe
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
