@@ -16,8 +16,8 @@ partitioned over the GPUs (strong scaling: BASELINE config 3 is "128 walkers at 
 `e2e`    : evals/s through network.log_likelihood_batch(host numpy theta) -- H2D of theta and
            D2H of the results inside the timed region.
 `roofline`: the kernel with the largest share of the step.  On the default path that is either the panel solve
-           (trsm_kernel: DMMA.8x8x4 GEMM against the explicit inverse with digit extraction fused; executed flops
-           against the FP64 tensor issue peak measured in this run) or the trailing update (syrk_i8_persistent_kernel:
+           (trsm_kernel: DMMA.8x8x4 GEMM against the explicit inverse with digit extraction fused; algorithmic flops
+           of the triangular solves that were executed, against the FP64 tensor issue peak measured in this run) or the trailing update (syrk_i8_persistent_kernel:
            exact integer products of 7-bit slices on tcgen05.mma.kind::i8; EXECUTED INT8 ops against the kind::i8
            issue peak measured in this run); the other one is reported as `roofline_update` / `roofline_panel_solve`.
            Both kernels leave out work that is exactly / provably nothing: K steps whose digit chunks are all zero,
@@ -596,7 +596,10 @@ def main():
             halves = skip[2] / 2.0
             scale = W_local * p / (skip[2] / (2.0 * sum(nblk - k - 1 for k in range(nblk)))) if skip[2] > 0 else 1.0
             right_done, left_done = halves - skip[4], halves - (skip[3] - skip[4])
-            trsm_flops = scale * (right_done * 2.0 * 128 * 64 * 128 + left_done * 2.0 * 128 * 64 * 64)
+            # ALGORITHMIC flops of the triangular solve X L^T = C for the halves that were solved: column c of X costs 2 (c + 1) flops
+            # per row -> right half (c = 64 .. 127) 2 x 128 x 64 x 96.5, left half (c = 0 .. 63) 2 x 128 x 64 x 32.5 (the kernel's GEMM
+            # against the explicit inverse executes k extents 104 and 40 on average)
+            trsm_flops = scale * (right_done * 2.0 * 128 * 64 * 96.5 + left_done * 2.0 * 128 * 64 * 32.5)
             trsm_tf = trsm_flops / (phase[3] * 1e-3) / 1e12 if phase[3] > 0 else None
             roofline_panel = {
                 "bound": "tensor",
@@ -604,11 +607,12 @@ def main():
                 "achieved": trsm_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": (trsm_tf / dmma_peak) if trsm_tf else None,
                 "peak_source": "DMMA.8x8x4 issue peak measured in this run (agpn_dmma_peak); MEASURED_PEAKS.json has no FP64 figure",
                 "flops_per_step": trsm_flops, "tile_halves": skip[2] * scale, "tile_halves_left_out": skip[3] * scale,
+                "right_halves_solved": right_done * scale, "left_halves_solved": left_done * scale,
                 "ms": float(phase[3]), "launches": int(nl[3]), "share_of_step_ms": float(phase[3] / max(step_prof_ms, 1e-9)),
                 "traffic": trsm_traffic,
                 "traffic_note": "DRAM bytes of all trsm_kernel launches of one step, ncu pass in profiles/ (scaled by walkers)",
-                "note": "EXECUTED GEMM flops of the halves that were solved; halves whose entries are bounded below 2^-96 of "
-                        "their row scale are left out after a read-only bound pass (AGPN_TRSM_SKIP=0: none)"}
+                "note": "ALGORITHMIC flops of the triangular solve (2 (c + 1) per row and column c) for the tile halves that were "
+                        "solved; halves whose entries are bounded below 2^-96 of their row scale are left out (AGPN_TRSM_SKIP=0: none)"}
             # `roofline` = the kernel with the largest share of the step
             roofline = roofline_panel if phase[3] > phase[4] else roofline_update
             second_roofline = ("roofline_update", roofline_update) if roofline is roofline_panel else ("roofline_panel_solve", roofline_panel)
