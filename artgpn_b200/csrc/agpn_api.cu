@@ -186,7 +186,7 @@ struct agpn_ctx {
     int wave_nmat = 0;                          // matrices of the last wave
     // panel solves with one CTA per 64-column half of a tile (AGPN_TRSM_SPLIT=0: one CTA per tile)
     bool trsm_split = true;
-    bool trsm_split_fixed = false;  // AGPN_TRSM_SPLIT given: for every batch size (default: fewer than 144 matrices only)
+    bool trsm_split_fixed = false;  // AGPN_TRSM_SPLIT given: for every batch size (default: matrices x block columns < 2304 only)
     double* d_rslot = nullptr;     // [cap_mats][nblk][2][2][128] parked forward-solve sums of the split panel solves
     // persistent tile-task kernel (agpn_mega.cuh): one launch per wave instead of the per-column chain; opt-in
     bool use_mega = false;         // AGPN_MEGA=1 enables it (measured: 23.9 vs 21.1 ms at 128 walkers, 3.66 vs 3.24 ms at 16)
@@ -962,7 +962,8 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
         const bool mega_wave = mega_eligible(c) && c->d_mega && !c->profiling && !c->timeline;
         // (measured with the banded schedule, 3 x 2048: split wins below ~ 40 walkers -- 16 walkers 2.11 vs 2.17 ms -- and loses
         // above, where half of its CTAs only find out that there is nothing to do: 128 walkers 11.29 vs 11.00 ms)
-        if (c->trsm_split && (c->trsm_split_fixed || nmat < 144) && c->d_rslot && c->i8_which == 3 && c->fuse_slices &&
+        // by tiles per launch, matrices x block columns: 3 x 8192, 32 walkers: 33.7 unsplit vs 34.8 ms split; 4 walkers: 7.96 vs 7.30)
+        if (c->trsm_split && (c->trsm_split_fixed || (long long)nmat * c->nblk < 144 * 16) && c->d_rslot && c->i8_which == 3 && c->fuse_slices &&
             c->i8_group >= c->nblk && !mega_wave) g.rslot = c->d_rslot;
         c->mask_nmat = 0;
         c->wave_nmat = (int)nmat;
