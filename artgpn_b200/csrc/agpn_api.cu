@@ -644,6 +644,8 @@ static int ensure_batch_workspace(agpn_ctx* c, size_t nmat, size_t W) {
                         make_batch_map(&c->tmB, c->d_A, nmat, c->npad, c->npad, BN);
         c->linv_blocks = mega_eligible(c) ? c->nblk : 1;
         CUDA_TRY(cudaMalloc(&c->d_Linv, sizeof(double) * nmat * c->linv_blocks * TB * TB));
+        // potrf_diag_kernel writes the lower block triangle of an inverse only: the zeros above it are put here once
+        CUDA_TRY(cudaMemset(c->d_Linv, 0, sizeof(double) * nmat * c->linv_blocks * TB * TB));
         CUDA_TRY(cudaMalloc(&c->d_rhs, sizeof(double) * nmat * np));
         CUDA_TRY(cudaMalloc(&c->d_logdet, sizeof(double) * nmat));
         CUDA_TRY(cudaMalloc(&c->d_quad, sizeof(double) * nmat));
@@ -1629,6 +1631,7 @@ static int predict_impl(agpn_ctx* c, const double* theta, int series, int M, con
         c->d_LinvAll = nullptr;
         c->cap_linv_blocks = 0;
         CUDA_TRY(cudaMalloc(&c->d_LinvAll, sizeof(double) * (size_t)c->nblk * TB * TB));
+        CUDA_TRY(cudaMemset(c->d_LinvAll, 0, sizeof(double) * (size_t)c->nblk * TB * TB));
         c->cap_linv_blocks = c->nblk;
     }
     if (Mpad * np > c->cap_V) {
@@ -1979,6 +1982,7 @@ extern "C" int agpn_potrf_batched(int device, int nmat, int n_pad, double* A, do
     CUDA_TRY(cudaMemsetAsync(b_refine.p, 0, sizeof(int) * nmat, st));
     CUDA_TRY(b_linv.alloc((size_t)nmat * TB * TB));
     double* d_linv = b_linv.p;
+    CUDA_TRY(cudaMemsetAsync(d_linv, 0, sizeof(double) * (size_t)nmat * TB * TB, st));     // zeros above the block diagonal of the inverse
     CUDA_TRY(cudaMemsetAsync(logdet, 0, sizeof(double) * nmat, st));
     if (quad) CUDA_TRY(cudaMemsetAsync(quad, 0, sizeof(double) * nmat, st));
     CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int) * nmat, st));

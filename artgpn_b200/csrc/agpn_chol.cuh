@@ -1076,11 +1076,12 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
     }
     grp_sync<G>();
 
-    // ---- rest of the inverse: the 16 x 16 diagonal blocks and the zeros above them (the blocks below were stored by step 2) ----
-    for (int R = tid >> 7; R < TB; R += 2) {
-        const int C = tid & 127;
-        if ((C >> 4) == (R >> 4)) Linv[R * TB + C] = Dv[(R >> 4) * 16 * PD_DV_LD + (R & 15) * PD_DV_LD + (C & 15)];
-        else if (C > R) Linv[R * TB + C] = 0.0;
+    // ---- rest of the inverse: the 16 x 16 diagonal blocks as full squares (the blocks below were stored by step 2).  The blocks
+    //      ABOVE the diagonal blocks are zero and nobody ever writes anything else there: every Linv buffer is cleared once when
+    //      it is allocated (agpn_api.cu), not 64 KB of zeros per factorised block (15 % of this kernel's stall samples) ----------
+    for (int e = tid; e < 8 * 16 * 16; e += 256) {
+        const int b = e >> 8, rr = (e >> 4) & 15, cc = e & 15;
+        Linv[(16 * b + rr) * TB + 16 * b + cc] = Dv[b * 16 * PD_DV_LD + rr * PD_DV_LD + cc];
     }
 
     // ---- z_k = Linv r_k ; |z_k|^2 ; sum log L_jj ------------------------------------------------------
