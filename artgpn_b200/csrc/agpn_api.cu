@@ -942,6 +942,7 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     g.info = d_infoflag;
     g.refine = c->d_info + 3 * c->cap_mats; g.refine_ratio = c->refine_ratio;
     g.A0 = c->d_A; g.mat0 = 0;
+    g.store_diag = 0;                           // a wave's results are log-det and quadratic form; the next wave re-assembles A
     c->group_eff = (c->group_fixed || (long long)nmat * c->nblk >= 384) ? c->group : 2;
     // two block columns: a single depth-128 update, where the per-tile cost of the INT8 kernel still outweighs its
     // rate (measured at 3 x 256, 256 walkers: 0.77 vs 0.73 ms); from three block columns on it wins (3 x 384: 1.43 vs 1.45 ms)

@@ -56,6 +56,7 @@ struct CholArgs {
     signed char* S8 = nullptr;  // [nmat] digit planes of the current group's block columns
     int sgroup = 0;             // block columns the slice storage of one matrix holds
     int keep_factor = 0;        // 1: the FP64 panels of L are stored even when only the digit planes are read again
+    int store_diag = 1;         // 0: the factored diagonal blocks are not written back (nobody reads them: likelihood waves)
     int* i8flag = nullptr;      // [nmat] or nullptr: set when a panel entry exceeds its row scale (digits would wrap)
     // ill-conditioned diagonal blocks: potrf_diag_kernel sets refine[mat] when max L_jj > refine_ratio * min L_jj for the
     // block it has just factorised; trsm_kernel then solves that block column by substitution (backward stable, like
@@ -964,16 +965,6 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
         }
     }
 
-    // ---- write L back (lower triangle incl. diagonal) -----------------------------------------------
-    for (int i = tid >> 6; i < TB; i += 4) {               // 16-byte stores; the element right of the diagonal is a zero
-        const int c = 2 * (tid & 63);
-        if (c <= i) {
-            double2 v = *reinterpret_cast<const double2*>(S + i * PD_LD + c);
-            if (c + 1 > i) v.y = 0.0;
-            *reinterpret_cast<double2*>(Akk + (size_t)i * ld + c) = v;
-        }
-    }
-
     double* Linv = g.Linv + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * (TB * TB);
     // ---- inverse, step 1: the eight 16 x 16 diagonal inverses, warp w -> block w, lane c -> column c --
     {
@@ -1075,6 +1066,20 @@ __device__ __forceinline__ void potrf_diag_body(const CholArgs& g, int k, int ma
         }
     }
     grp_sync<G>();
+
+    // ---- write L back (lower triangle incl. diagonal; the strict upper triangle of S holds the transposed inverse by now).
+    //      On the likelihood path nobody reads the factored diagonal block again (log-det and z are taken here) unless the
+    //      panel solve has to substitute with it: store_diag = 0 leaves it out then -----------------------------------------
+    if (g.store_diag || s_refine) {
+        for (int i = tid >> 6; i < TB; i += 4) {           // 16-byte stores; the element right of the diagonal is a zero
+            const int c = 2 * (tid & 63);
+            if (c <= i) {
+                double2 v = *reinterpret_cast<const double2*>(S + i * PD_LD + c);
+                if (c + 1 > i) v.y = 0.0;
+                *reinterpret_cast<double2*>(Akk + (size_t)i * ld + c) = v;
+            }
+        }
+    }
 
     // ---- rest of the inverse: the 16 x 16 diagonal blocks as full squares (the blocks below were stored by step 2).  The blocks
     //      ABOVE the diagonal blocks are zero and nobody ever writes anything else there: every Linv buffer is cleared once when
