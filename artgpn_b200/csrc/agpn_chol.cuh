@@ -688,6 +688,8 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
             signed char* S = g.S8 + (size_t)mat * i8_slices_per_matrix(g.nblk, g.sgroup);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
+                // a chunk without a non-zero digit is never read when the update goes by the masks: its store is left out
+                if (g.nzmask != nullptr && !s_nz[c]) continue;
                 uint4* dstg = reinterpret_cast<uint4*>(S + i8_tile_off(4 * (k - k0) + 2 * h + c, ti, g.nblk));
                 const uint4* src = reinterpret_cast<const uint4*>(stg + c * I8_TILE_BYTES);
 #pragma unroll
