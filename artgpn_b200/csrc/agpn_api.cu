@@ -996,7 +996,8 @@ static int enqueue_wave(agpn_ctx* c, int Ww, const double* d_theta, double* d_ou
     // where every launch fills the GPU by itself and fewer, larger launches pay fewer tails (measured, 3 x 2048: 128 walkers
     // 20.60 / 20.66 / 20.80 ms with 3 / 4 / 6 streams, 64 walkers 10.56 vs 10.66 with 4 vs 6, 16 walkers 3.32 vs 3.20)
     int nsub_pref = c->nsub;
-    if (!c->nsub_fixed) nsub_pref = nmat >= 288 ? 3 : (nmat >= 144 ? 4 : c->nsub);
+    // (banded schedule, shorter kernels: 128 walkers 10.53 / 10.78 ms with 2 / 3 streams, 64 walkers 5.71 / 5.76 with 3 / 4)
+    if (!c->nsub_fixed) nsub_pref = nmat >= 288 ? 2 : (nmat >= 144 ? 3 : c->nsub);
     const int nsub = (c->profiling || nsub_pref < 2 || nmat < 2 * nsub_pref) ? 1 : nsub_pref;
     if (mega_eligible(c) && g.S8 && c->d_mega && !c->profiling && !c->timeline) {
         // the whole factorisation as ONE persistent launch of tile tasks (agpn_mega.cuh)

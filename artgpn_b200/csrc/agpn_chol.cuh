@@ -546,20 +546,35 @@ __device__ __forceinline__ void trsm_body(const CholArgs& g, int k, int k0, int 
     bool skip_h[2] = {false, false};
     if (g.linvnorm != nullptr && g.nzmask != nullptr && (flags & 1) && !refine) {
         // bound the half before touching the tensor pipe: |X_ic| <= max_j |C_ij| * ||rows of Linv of this half||_inf
+        // everything the decision reads is fetched up front, independent of each other: one global-memory latency, not a chain
+        // of three (this is all a CTA whose half is left out ever does, and it delays the pipeline fill of the others)
         const double* ln = g.linvnorm + ((size_t)mat * g.linv_blocks + (g.linv_blocks > 1 ? k : 0)) * 2;
-        const double thr0 = TRSM_SKIP_BOUND / ln[0], thr1 = TRSM_SKIP_BOUND / ln[1];     // norm inf / NaN: nothing passes
+        const double ln0 = ln[0], ln1 = ln[1];
+        const unsigned long long bU = (g.tmaxU != nullptr) ? g.tmaxU[((size_t)mat * g.nblk + ti) * g.nblk + k] : 0ull;
+        const double bA = (g.tmaxA != nullptr && k0 == 0)
+            ? g.tmaxA[(size_t)mat * ((size_t)g.nblk * (g.nblk + 1) / 2) + (size_t)ti * (ti + 1) / 2 + k] : -1.0;
+        unsigned long long act = 0ull;                          // any K step of the update on this tile active?  (k > k0)
+        {
+            const int nks = 4 * (k - k0);
+            const unsigned long long* mi_ = g.nzmask + ((size_t)mat * g.nblk + ti) * g.nzwords;
+            const unsigned long long* mk_ = g.nzmask + ((size_t)mat * g.nblk + k) * g.nzwords;
+            for (int wd = 0; wd * 64 < nks; ++wd) {
+                unsigned long long a = mi_[wd] & mk_[wd];
+                const int left = nks - wd * 64;
+                if (left < 64) a &= (1ull << left) - 1ull;
+                act |= a;
+            }
+        }
+        const double thr0 = TRSM_SKIP_BOUND / ln0, thr1 = TRSM_SKIP_BOUND / ln1;     // norm inf / NaN: nothing passes
         int bad0 = 0, bad1 = 0;
         // without reading the tile: the update has just rewritten it and recorded max |C_ij| Q / r_i, or no K step of it was
         // active (same mask test as the update kernel) and it still holds the assembled entries, bounded by tmaxA
         double known = -1.0;                                    // bound on |C_ij| (x Q / r_i if `scaled`), < 0: unknown
         bool scaled = false;
-        if (k > k0 && i8_any_active(g, mat, ti, k, 4 * (k - k0))) {
-            if (g.tmaxU != nullptr) {
-                const unsigned long long b = g.tmaxU[((size_t)mat * g.nblk + ti) * g.nblk + k];
-                if (b != 0ull) { known = __longlong_as_double((long long)b); scaled = true; }
-            }
-        } else if (g.tmaxA != nullptr && k0 == 0) {
-            known = g.tmaxA[(size_t)mat * ((size_t)g.nblk * (g.nblk + 1) / 2) + (size_t)ti * (ti + 1) / 2 + k];
+        if (act != 0ull) {
+            if (bU != 0ull) { known = __longlong_as_double((long long)bU); scaled = true; }
+        } else {
+            known = bA;
         }
         if (known >= 0.0) {                                      // false for NaN
             if (tid < TB) {
