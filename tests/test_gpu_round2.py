@@ -402,7 +402,7 @@ def test_nothing_is_skipped_when_the_covariance_does_not_decay(monkeypatch):
 
 
 def test_skipping_with_sub_batch_streams(monkeypatch):
-    """144 matrices run as four sub-batches on their own streams, each with its slice of the masks and inverse norms:
+    """144 matrices run as several sub-batches on their own streams, each with its slice of the masks and inverse norms:
     same bits as the dense schedule."""
     from artgpn_b200 import synth
     N = 700
