@@ -220,8 +220,9 @@ __device__ __forceinline__ void gemm_load_stage(double* stage, const double* __r
 }
 
 // NI0: first of the warp's four 8-column groups that takes part (2: the triangular operand's rows of groups 0 and 1 are zero
-// in this k-chunk)
-template <int NI0 = 0>
+// in this k-chunk); NIH: group whose rows are zero in the second half of the chunk (its diagonal 8 x 8 block sits in the first
+// half), -1: none
+template <int NI0 = 0, int NIH = -1>
 __device__ __forceinline__ void gemm_compute_stage(const double* stage, double (&acc)[4][4][2], int wm, int wn, int lane) {
     const double* As = stage;
     const double* Bs = stage + TB * GEMM_KC;
@@ -234,11 +235,13 @@ __device__ __forceinline__ void gemm_compute_stage(const double* stage, double (
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = As[swz(wm * 32 + mi * 8 + r, k)];
 #pragma unroll
-        for (int ni = NI0; ni < 4; ++ni) b[ni] = Bs[swz(wn * 32 + ni * 8 + r, k)];
+        for (int ni = NI0; ni < 4; ++ni)
+            if (!(ni == NIH && ks >= GEMM_KC / 8)) b[ni] = Bs[swz(wn * 32 + ni * 8 + r, k)];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = NI0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            for (int ni = NI0; ni < 4; ++ni)
+                if (!(ni == NIH && ks >= GEMM_KC / 8)) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
 }
 
@@ -324,7 +327,8 @@ __device__ __forceinline__ void gemm_nt_prologue(const GemmPipe& p, const double
 // kc_limit: this warp's operand columns are exactly zero from k-chunk kc_limit on (triangular B): it skips the tensor
 // work of those chunks but still takes part in the loads and the barriers.  tri: B is lower triangular with its diagonal
 // running through the warp's last two chunks (16 columns each against the warp's 32 rows of B): in the last one the first two
-// 8-row groups of B are zero as well.
+// 8-row groups of B are zero as well, and in each of the two the group whose diagonal 8 x 8 block lies in the chunk's first half
+// is zero in its second half.
 template <bool G = false>
 __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __restrict__ Ag, int lda,
                                                  const double* __restrict__ Bg, int ldb, int K, double (&acc)[4][4][2],
@@ -348,7 +352,8 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmPipe& p, const double* __re
 #else
         mbar_wait(p.full + 8 * s, (n / GEMM_STAGES) & 1);
         if (active && kc < kc_limit) {
-            if (tri && kc == kc_limit - 1) gemm_compute_stage<2>(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+            if (tri && kc == kc_limit - 1) gemm_compute_stage<2, 2>(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
+            else if (tri && kc == kc_limit - 2) gemm_compute_stage<0, 0>(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
             else gemm_compute_stage(smem + s * GEMM_STAGE_DOUBLES, acc, wm, wn, lane);
         }
         __syncwarp();
